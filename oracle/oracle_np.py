@@ -1,0 +1,239 @@
+"""Independent numpy/scipy twin of oracle/oracle.cpp.  TEST INFRASTRUCTURE ONLY.
+
+Second restatement of the same reference algebra (RegridMatrices_Dynamic.cpp:50-332, IceRegridder_L0.cpp:100-214,
+IceRegridder.cpp:41-65, modele/hntr.cpp:84-168, modele/hntr.hpp:204-435) written against scipy.sparse instead of
+hand-rolled CSC, so that a misreading shared by both is less likely.  Pure-Python loops: small cases only.
+"""
+import math
+
+import numpy as np
+import scipy.sparse as sp
+
+
+class SparseSet:
+    def __init__(self, ids=None):
+        self.to_d = {}
+        self.to_s = []
+        for s in ([] if ids is None else ids):
+            self.add(int(s))
+
+    def add(self, s):
+        d = self.to_d.get(s)
+        if d is None:
+            d = len(self.to_s)
+            self.to_d[s] = d
+            self.to_s.append(s)
+        return d
+
+    def __len__(self):
+        return len(self.to_s)
+
+
+def _interp(hc, elev):
+    n = len(hc)
+    hi = int(np.searchsorted(hc, elev, side="left"))     # std::lower_bound
+    hi = max(hi, 1)
+    if hi >= n:
+        raise ValueError("Elevation %g out of bounds" % elev)
+    lo = hi - 1
+    ratio = (elev - hc[lo]) / (hc[hi] - hc[lo])
+    return (lo, hi), (1.0 - ratio, ratio)
+
+
+def _gen(kind, gridA, sheet, hc, em):
+    """Generator tuples (i_sparse, j_sparse, value) for gridG == 'X'."""
+    out = []
+    nA = gridA.nA
+    for x in range(sheet.nX):
+        a, i = int(sheet.ex_ij[x, 0]), int(sheet.ex_ij[x, 1])
+        if math.isnan(em[i]):
+            continue
+        s = float(sheet.ex_area[x])
+        if kind == "GvI":
+            out.append((x, i, s))
+        elif kind == "GvAp":
+            if s > 0:
+                out.append((x, a, s))
+        else:
+            (k0, k1), (w0, w1) = _interp(hc, max(float(em[i]), 0.0))
+            if w0 != 0:
+                out.append((x, k0 * nA + a, s * w0))
+            if w1 != 0:
+                out.append((x, k1 * nA + a, s * w1))
+    return out
+
+
+def _diag_gen(kind, gridA, sheet, nhc):
+    out = []
+    for d, a in enumerate(gridA.dim):
+        r = gridA.native_area[d] / sheet.gridA_proj_area[d]
+        if kind == "A":
+            out.append((int(a), r))
+        else:
+            out.extend((k * gridA.nA + int(a), r) for k in range(nhc))
+    return out
+
+
+def _dense(gen, d0, d1):
+    r = [d0.add(t[0]) for t in gen]
+    c = [d1.add(t[1]) for t in gen]
+    v = [t[2] for t in gen]
+    return r, c, v
+
+
+def _mat(rcv, n0, n1, transpose=False):
+    r, c, v = rcv
+    M = sp.coo_matrix((v, (r, c)), shape=(n0, n1)).tocsc()
+    M.sum_duplicates()
+    return M.T.tocsc() if transpose else M
+
+
+def _diag(gen, dim):
+    v = np.zeros(len(dim))
+    for s, r in gen:
+        d = dim.to_d.get(s)
+        if d is not None:
+            v[d] = r
+    return v
+
+
+def _rows(M):
+    return np.asarray(M.sum(axis=1)).ravel()
+
+
+def _cols(M):
+    return np.asarray(M.sum(axis=0)).ravel()
+
+
+def matrix(gridA, sheet, hc, em, spec, scale=True, correctA=False, dims=(None, None)):
+    """Returns dict(M=csc, wM, Mw, dims=[ids0, ids1]) with the reference's dense numbering."""
+    b, a = spec[0], spec[2]
+    nhc = len(hc)
+    dG = SparseSet()
+    dB, dA = SparseSet(dims[0]), SparseSet(dims[1])
+    gen = {k: None for k in ("GvI", "GvAp", "GvEp")}
+
+    def g(kind):
+        if gen[kind] is None:
+            gen[kind] = _gen(kind, gridA, sheet, hc, em)
+        return gen[kind]
+    ur = {"A": ("GvAp", "A"), "E": ("GvEp", "E")}
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if b in "AE" and a == "I":
+            t1 = _dense(g(ur[b][0]), dG, dB)
+            t2 = _dense(g("GvI"), dG, dA)
+            ApvG = _mat(t1, len(dG), len(dB), True)
+            GvI = _mat(t2, len(dG), len(dA))
+            ApvI = (ApvG @ sp.diags(1.0 / _rows(GvI))) @ GvI
+            Mw = _cols(ApvI)
+            wApvI = _rows(ApvI)
+            if correctA:
+                w = _diag(_diag_gen(ur[b][1], gridA, sheet, nhc), dB)
+                wM = w * wApvI
+                M = sp.diags((1.0 / w) * (1.0 / wApvI)) @ ApvI if scale else ApvI
+            else:
+                wM = wApvI
+                M = sp.diags(1.0 / wApvI) @ ApvI if scale else ApvI
+        elif b == "I" and a in "AE":
+            t1 = _dense(g(ur[a][0]), dG, dA)
+            t2 = _dense(g("GvI"), dG, dB)
+            GvAp = _mat(t1, len(dG), len(dA))
+            IvG = _mat(t2, len(dG), len(dB), True)
+            IvAp = (IvG @ sp.diags(1.0 / _rows(GvAp))) @ GvAp
+            wM = _rows(IvAp)
+            if correctA:
+                s = _diag(_diag_gen(ur[a][1], gridA, sheet, nhc), dA)
+                Mw = s * _cols(IvAp)
+                M = (sp.diags(1.0 / wM) @ IvAp if scale else IvAp) @ sp.diags(s)
+            else:
+                Mw = _cols(IvAp)
+                M = sp.diags(1.0 / wM) @ IvAp if scale else IvAp
+        elif (b, a) in (("E", "A"), ("A", "E")):
+            tA = _dense(g(ur[a][0]), dG, dA)
+            tE = _dense(g(ur[b][0]), dG, dB)
+            GvAp = _mat(tA, len(dG), len(dA))
+            EpvG = _mat(tE, len(dG), len(dB), True)
+            EpvAp = (EpvG @ sp.diags(1.0 / _rows(GvAp))) @ GvAp
+            wE = _rows(EpvAp)
+            if correctA:
+                sA = _diag(_diag_gen(ur[a][1], gridA, sheet, nhc), dA)
+                sE = _diag(_diag_gen(ur[b][1], gridA, sheet, nhc), dB)
+                wM = sE * wE
+                Mw = sA * _cols(EpvAp)
+                M = (sp.diags(1.0 / wM) @ EpvAp if scale else EpvAp) @ sp.diags(sA)
+            else:
+                wM, Mw = wE, _cols(EpvAp)
+                M = sp.diags(1.0 / wE) @ EpvAp if scale else EpvAp
+        else:
+            raise KeyError(spec)
+    M = sp.csc_matrix(M)
+    M.sort_indices()
+    return dict(M=M, wM=wM, Mw=Mw, dims=[np.array(dB.to_s, np.int64), np.array(dA.to_s, np.int64)])
+
+
+# ----------------------------------------------------------------------------------------------
+class Hntr:
+    """Loop-for-loop numpy twin of the Hntr partition + regrid; spec = (im, jm, offi, dlat_minutes)."""
+
+    def __init__(self, specB, specA, datmis=0.0):
+        (imB, jmB, offB, dlB), (imA, jmA, offA, dlA) = specB, specA
+        self.specB, self.specA, self.datmis = specB, specA, datmis
+        self.IMIN = np.zeros(imB, int); self.IMAX = np.zeros(imB, int)
+        self.FMIN = np.zeros(imB); self.FMAX = np.zeros(imB)
+        ia, ria, prev = 1, (1 + offA - imA) * imB, imB
+        for ib in range(1, imB + 1):
+            rib = (ib - 1 + offB) * imA
+            while ria < rib:
+                ia += 1; ria += imB
+            if ria == rib:
+                self.IMAX[prev - 1], self.FMAX[prev - 1] = ia, 0.0
+                ia += 1; ria += imB
+                self.IMIN[ib - 1], self.FMIN[ib - 1] = ia, 0.0
+            else:
+                self.IMAX[prev - 1], self.FMAX[prev - 1] = ia, (ria - rib) / imB
+                self.IMIN[ib - 1], self.FMIN[ib - 1] = ia, 1 - self.FMAX[prev - 1]
+            prev = ib
+        self.IMAX[imB - 1] += imA
+        k = (2 * math.pi) / (360 * 60)
+        self.SINA = np.array([-1.0] + [math.sin((j + .5 - .5 * (1 + jmA)) * dlA * k) for j in range(1, jmA)] + [1.0])
+        self.SINB = np.array([-1.0] + [math.sin((j + .5 - .5 * (1 + jmB)) * dlB * k) for j in range(1, jmB)] + [1.0])
+        self.JMIN = np.zeros(jmB, int); self.JMAX = np.zeros(jmB, int)
+        self.GMIN = np.zeros(jmB); self.GMAX = np.zeros(jmB)
+        self.JMIN[0] = 1
+        ja = 1
+        for jb in range(1, jmB):
+            while self.SINA[ja] < self.SINB[jb]:
+                ja += 1
+            if self.SINA[ja] == self.SINB[jb]:
+                self.JMAX[jb - 1] = ja
+                ja += 1
+                self.JMIN[jb] = ja
+            else:
+                self.JMAX[jb - 1], self.GMAX[jb - 1] = ja, self.SINA[ja] - self.SINB[jb]
+                self.JMIN[jb], self.GMIN[jb] = ja, self.SINB[jb] - self.SINA[ja - 1]
+        self.JMAX[jmB - 1] = jmA
+
+    def regrid(self, WTA, A, mean_polar=False):
+        (imB, jmB, _, _), (imA, jmA, _, _) = self.specB, self.specA
+        A = np.asarray(A, float).reshape(jmA, imA)
+        W = np.ones_like(A) if WTA is None else np.asarray(WTA, float).reshape(jmA, imA)
+        B = np.zeros((jmB, imB))
+        for jb in range(jmB):
+            for ib in range(imB):
+                wsum = vsum = 0.0
+                for ja in range(self.JMIN[jb], self.JMAX[jb] + 1):
+                    G = self.SINA[ja] - self.SINA[ja - 1]
+                    if ja == self.JMIN[jb]: G -= self.GMIN[jb]
+                    if ja == self.JMAX[jb]: G -= self.GMAX[jb]
+                    for ir in range(self.IMIN[ib], self.IMAX[ib] + 1):
+                        F = 1.0
+                        if ir == self.IMIN[ib]: F -= self.FMIN[ib]
+                        if ir == self.IMAX[ib]: F -= self.FMAX[ib]
+                        wt = (F * G) * W[ja - 1, (ir - 1) % imA]
+                        wsum += wt
+                        vsum += wt * A[ja - 1, (ir - 1) % imA]
+                B[jb, ib] = self.datmis if wsum == 0 else vsum / wsum
+        if mean_polar:
+            for jb in {0, jmB - 1}:
+                B[jb, :] = self.datmis if np.any(B[jb] == self.datmis) else B[jb].sum() / imB
+        return B.ravel()
