@@ -1,0 +1,593 @@
+// capi.cu -- the extern "C" boundary declared in include/icebin_b200.h.  Thin: argument checks, host<->device
+// staging for the host-pointer entry points, exception -> status code translation.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "types.cuh"
+
+namespace ib {
+
+std::atomic<int64_t> g_launches{0};
+static thread_local std::string g_err;
+
+void ensure_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        fail(IB_ERR_CUDA, "icebin_b200: no CUDA device available (%s); there is no CPU fallback",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+}
+
+cudaStream_t default_stream()
+{
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    IB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (!streams[dev]) {
+        IB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+        // keep freed blocks in the pool: steady-state matrix builds then never reach the driver allocator
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    return streams[dev];
+}
+
+int sm_count()
+{
+    static int n[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    return n[dev] > 0 ? n[dev] : 148;
+}
+
+// hntr.cu
+struct Hntr;
+Hntr *hntr_create(int, int, double, double, int, int, double, double, double);
+void hntr_free(Hntr *);
+void hntr_get(Hntr const &, int, double *, int32_t *);
+void hntr_dims(Hntr const &, int *);
+void hntr_regrid_dev(Hntr &, const double *, double, double, const void *, int, double *, bool, cudaStream_t);
+int64_t hntr_matrix(Hntr &, double, int64_t *, int64_t *, double *, cudaStream_t);
+
+// cell-major <-> field-major transposition: out[c*ldo + r] = in[r*ldi + c]
+__global__ void transpose_kernel(const double *__restrict__ in, int64_t ldi, int64_t nr, int64_t nc, double *__restrict__ out, int64_t ldo)
+{
+    __shared__ double tile[32][33];
+    int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int64_t r = r0 + k, c = c0 + threadIdx.x;
+        if (r < nr && c < nc) tile[k][threadIdx.x] = in[r * ldi + c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int64_t c = c0 + k, r = r0 + threadIdx.x;
+        if (r < nr && c < nc) out[c * ldo + r] = tile[threadIdx.x][k];
+    }
+}
+static void transpose(const double *in, int64_t ldi, int64_t nr, int64_t nc, double *out, int64_t ldo, cudaStream_t s)
+{
+    if (nr == 0 || nc == 0) return;
+    dim3 grid((unsigned)cdiv(nc, 32), (unsigned)cdiv(nr, 32)), block(32, 8);
+    transpose_kernel<<<grid, block, 0, s>>>(in, ldi, nr, nc, out, ldo);
+    IB_LAUNCHED();
+}
+
+// gather/scatter between sparse-indexed field-major host layout and dense cell-major device layout (apply_M)
+__global__ void densify_kernel(const double *__restrict__ As, int64_t nsparse, const int64_t *__restrict__ sparse_of, int identity,
+                               int64_t ndense, int nvar, double *__restrict__ Xd)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t d = t % ndense;
+    int64_t f = t / ndense;
+    if (f >= nvar) return;
+    int64_t sidx = identity ? d : sparse_of[d];
+    Xd[d * nvar + f] = As[f * nsparse + sidx];
+}
+__global__ void sparsify_kernel(const double *__restrict__ Yd, const int64_t *__restrict__ sparse_of, int identity, int64_t ndense,
+                                int nvar, int64_t nsparse, double *__restrict__ Bs)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t d = t % ndense;
+    int64_t f = t / ndense;
+    if (f >= nvar) return;
+    int64_t sidx = identity ? d : sparse_of[d];
+    Bs[f * nsparse + sidx] = Yd[d * nvar + f];
+}
+__global__ void fill_f64_kernel(double *p, int64_t n, double v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}   // namespace ib
+
+using namespace ib;
+
+#define IB_TRY try {
+#define IB_CATCH                                                           \
+    }                                                                      \
+    catch (ib::Error const &e) { g_err = e.what(); return e.code; }        \
+    catch (std::exception const &e) { g_err = e.what(); return IB_ERR_ARG; }
+
+struct ib_gcm { Gcm g; };
+struct ib_rm { RegridMatrices r; };
+struct ib_dim { Dim d; };
+struct ib_weighted { std::unique_ptr<Weighted> w; };
+struct ib_hntr { ib::Hntr *h; };
+
+extern "C" {
+
+const char *ib_last_error(void) { return g_err.c_str(); }
+
+int ib_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int ib_set_device(int device)
+{
+    IB_TRY
+    IB_CUDA(cudaSetDevice(device));
+    return IB_OK;
+    IB_CATCH
+}
+int64_t ib_launch_count(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------------------- GCMRegridder
+int ib_gcm_create(ib_gcm **out, int64_t nA, int32_t n_real, const int64_t *dimA, const double *native_area, int32_t nhc,
+                  const double *hcdefs, int correctA)
+{
+    IB_TRY
+    if (!out || nA <= 0 || n_real < 0 || nhc < 0 || (n_real && (!dimA || !native_area)) || (nhc && !hcdefs))
+        fail(IB_ERR_ARG, "ib_gcm_create: bad argument");
+    ensure_device();
+    std::unique_ptr<ib_gcm> G(new ib_gcm);
+    Gcm &g = G->g;
+    g.nA = nA; g.correctA = correctA;
+    g.dimA_h.assign(dimA, dimA + n_real);
+    for (int64_t v : g.dimA_h) if (v < 0 || v >= nA) fail(IB_ERR_ARG, "ib_gcm_create: A cell index %ld outside [0,%ld)", (long)v, (long)nA);
+    g.native_area_h.assign(native_area, native_area + n_real);
+    g.hcdefs_h.assign(hcdefs, hcdefs + nhc);
+    for (int k = 1; k < nhc; ++k) if (!(hcdefs[k] > hcdefs[k - 1])) fail(IB_ERR_ARG, "ib_gcm_create: hcdefs must be strictly increasing");
+    cudaStream_t s = default_stream();
+    g.hcdefs.alloc((size_t)nhc, s);
+    g.hcdefs.upload(g.hcdefs_h.data(), (size_t)nhc);
+    IB_CUDA(cudaStreamSynchronize(s));
+    *out = G.release();
+    return IB_OK;
+    IB_CATCH
+}
+void ib_gcm_free(ib_gcm *g) { delete g; }
+
+int ib_gcm_add_sheet(ib_gcm *G, const char *name, int64_t nI, int32_t n_real_I, const int64_t *dimI, const double *native_areaI,
+                     const double *centroid_xy, int64_t nX, const int32_t *ex_ij, const double *ex_area,
+                     const double *gridA_proj_area, int interp_style)
+{
+    IB_TRY
+    if (!G || nI <= 0 || n_real_I < 0 || nX < 0 || (nX && (!ex_ij || !ex_area)) || !gridA_proj_area)
+        fail(IB_ERR_ARG, "ib_gcm_add_sheet: bad argument");
+    if (interp_style != IB_Z_INTERP && interp_style != IB_ELEV_CLASS_INTERP) fail(IB_ERR_ARG, "ib_gcm_add_sheet: unknown interp_style");
+    Gcm &g = G->g;
+    for (int64_t x = 0; x < nX; ++x) {
+        if (ex_ij[2 * x] < 0 || ex_ij[2 * x] >= g.nA || ex_ij[2 * x + 1] < 0 || ex_ij[2 * x + 1] >= nI)
+            fail(IB_ERR_ARG, "ib_gcm_add_sheet: exchange cell %ld references (iA=%d, iI=%d) outside the grids", (long)x, ex_ij[2 * x], ex_ij[2 * x + 1]);
+    }
+    cudaStream_t s = default_stream();
+    std::unique_ptr<Sheet> sh(new Sheet);
+    sh->name = name ? name : "icesheet";
+    sh->nI = nI; sh->nX = nX; sh->interp_style = interp_style;
+    sh->dimI_h.assign(dimI, dimI + n_real_I);
+    sh->dimI_identity = (n_real_I == nI);
+    for (int64_t i = 0; i < n_real_I && sh->dimI_identity; ++i) sh->dimI_identity = (dimI[i] == i);
+    sh->dimI.alloc((size_t)n_real_I, s); sh->dimI.upload(dimI, (size_t)n_real_I);
+    sh->native_areaI.alloc((size_t)n_real_I, s); sh->native_areaI.upload(native_areaI, (size_t)n_real_I);
+    if (centroid_xy) { sh->centroid_xy.alloc(2 * (size_t)n_real_I, s); sh->centroid_xy.upload(centroid_xy, 2 * (size_t)n_real_I); }
+    sh->ex_ij.alloc((size_t)nX, s); sh->ex_ij.upload(reinterpret_cast<const int2 *>(ex_ij), (size_t)nX);
+    sh->ex_area.alloc((size_t)nX, s); sh->ex_area.upload(ex_area, (size_t)nX);
+    // sApvA / sEpvE diagonal (IceRegridder.cpp:41-65): native/proj per realised A cell, 0 elsewhere ("missing")
+    std::vector<double> ratio((size_t)g.nA, 0.0);
+    sh->gridA_proj_area_h.assign(gridA_proj_area, gridA_proj_area + g.dimA_h.size());
+    for (size_t d = 0; d < g.dimA_h.size(); ++d) ratio[(size_t)g.dimA_h[d]] = g.native_area_h[d] / gridA_proj_area[d];
+    sh->ratioA.alloc((size_t)g.nA, s); sh->ratioA.upload(ratio.data(), ratio.size());
+    IB_CUDA(cudaStreamSynchronize(s));
+    g.sheets.push_back(std::move(sh));
+    return (int)g.sheets.size() - 1;
+    IB_CATCH
+}
+
+int64_t ib_gcm_nA(const ib_gcm *G) { return G->g.nA; }
+int64_t ib_gcm_nE(const ib_gcm *G) { return G->g.nE(); }
+int32_t ib_gcm_nhc(const ib_gcm *G) { return (int32_t)G->g.hcdefs_h.size(); }
+int ib_gcm_nsheets(const ib_gcm *G) { return (int)G->g.sheets.size(); }
+int ib_gcm_correctA(const ib_gcm *G) { return G->g.correctA; }
+int64_t ib_gcm_nI(const ib_gcm *G, int sheet) { return (sheet < 0 || sheet >= (int)G->g.sheets.size()) ? -1 : G->g.sheets[sheet]->nI; }
+int64_t ib_gcm_nX(const ib_gcm *G, int sheet) { return (sheet < 0 || sheet >= (int)G->g.sheets.size()) ? -1 : G->g.sheets[sheet]->nX; }
+int ib_gcm_sheet_index(const ib_gcm *G, const char *name)
+{
+    for (size_t i = 0; i < G->g.sheets.size(); ++i) if (G->g.sheets[i]->name == name) return (int)i;
+    g_err = std::string("no ice sheet named '") + name + "'";
+    return IB_ERR_ARG;
+}
+int ib_gcm_wA(const ib_gcm *G, int sheet, int native, int64_t *index, double *area)
+{
+    IB_TRY
+    Gcm const &g = G->g;
+    if (sheet < 0 || sheet >= (int)g.sheets.size()) fail(IB_ERR_ARG, "ib_gcm_wA: bad sheet index %d", sheet);
+    auto const &a = native ? g.native_area_h : g.sheets[sheet]->gridA_proj_area_h;
+    for (size_t d = 0; d < g.dimA_h.size(); ++d) { index[d] = g.dimA_h[d]; area[d] = a[d]; }
+    return IB_OK;
+    IB_CATCH
+}
+
+// ---------------------------------------------------------------------------------------- RegridMatrices
+static int regrid_matrices_impl(ib_gcm *G, int sheet, const double *em, bool on_device, int scale, int correctA, const double *sigma,
+                                cudaStream_t s, ib_rm **out)
+{
+    IB_TRY
+    if (!G || !em || !out) fail(IB_ERR_ARG, "ib_regrid_matrices: bad argument");
+    Gcm &g = G->g;
+    if (sheet < 0 || sheet >= (int)g.sheets.size()) fail(IB_ERR_ARG, "ib_regrid_matrices: bad sheet index %d", sheet);
+    ensure_device();
+    std::unique_ptr<ib_rm> R(new ib_rm);
+    R->r.gcm = &g; R->r.sheet = sheet;
+    R->r.params.scale = scale != 0; R->r.params.correctA = correctA != 0;
+    if (sigma) R->r.params.sigma = {sigma[0], sigma[1], sigma[2]};
+    R->r.stream = s;
+    size_t n = (size_t)g.sheets[sheet]->nI;
+    R->r.elevmaskI.alloc(n, s);
+    IB_CUDA(cudaMemcpyAsync(R->r.elevmaskI.p, em, n * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    if (!on_device) IB_CUDA(cudaStreamSynchronize(s));
+    *out = R.release();
+    return IB_OK;
+    IB_CATCH
+}
+int ib_regrid_matrices(ib_gcm *G, int sheet, const double *elevmaskI, int scale, int correctA, const double *sigma, ib_rm **out)
+{
+    cudaStream_t s;
+    IB_TRY s = default_stream(); IB_CATCH
+    return regrid_matrices_impl(G, sheet, elevmaskI, false, scale, correctA, sigma, s, out);
+}
+int ib_regrid_matrices_dev(ib_gcm *G, int sheet, const double *d_elevmaskI, int scale, int correctA, const double *sigma, void *stream,
+                           ib_rm **out)
+{
+    cudaStream_t s;
+    IB_TRY s = stream ? (cudaStream_t)stream : default_stream(); IB_CATCH
+    return regrid_matrices_impl(G, sheet, d_elevmaskI, true, scale, correctA, sigma, s, out);
+}
+void ib_rm_free(ib_rm *r) { delete r; }
+
+int ib_dim_create(ib_dim **out)
+{
+    IB_TRY
+    *out = new ib_dim;
+    return IB_OK;
+    IB_CATCH
+}
+int ib_dim_create_ids(ib_dim **out, int64_t sparse_extent, int64_t n, const int64_t *ids)
+{
+    IB_TRY
+    if (n < 0 || (n && !ids)) fail(IB_ERR_ARG, "ib_dim_create_ids: bad argument");
+    std::unique_ptr<ib_dim> D(new ib_dim);
+    D->d.pending.assign(ids, ids + n);
+    {   // ids must be distinct (a SparseSet is a bijection)
+        std::vector<int64_t> t(D->d.pending);
+        std::sort(t.begin(), t.end());
+        if (std::adjacent_find(t.begin(), t.end()) != t.end()) fail(IB_ERR_ARG, "ib_dim_create_ids: duplicate sparse id");
+    }
+    D->d.dense_extent = n;
+    D->d.sparse_extent = sparse_extent;
+    if (n == 0) D->d.pending.clear();
+    *out = D.release();
+    return IB_OK;
+    IB_CATCH
+}
+int ib_dim_create_identity(ib_dim **out, int64_t n)
+{
+    IB_TRY
+    if (n < 0) fail(IB_ERR_ARG, "ib_dim_create_identity: bad argument");
+    std::unique_ptr<ib_dim> D(new ib_dim);
+    D->d.identity = true; D->d.sparse_extent = n; D->d.dense_extent = n;
+    *out = D.release();
+    return IB_OK;
+    IB_CATCH
+}
+int64_t ib_dim_dense_extent(const ib_dim *d) { return d->d.dense_extent; }
+int64_t ib_dim_sparse_extent(const ib_dim *d) { return d->d.sparse_extent; }
+int ib_dim_get_ids(const ib_dim *d, int64_t *ids)
+{
+    IB_TRY
+    auto v = d->d.ids(d->d.sparse_of.st ? d->d.sparse_of.st : default_stream());
+    std::copy(v.begin(), v.end(), ids);
+    return IB_OK;
+    IB_CATCH
+}
+void ib_dim_free(ib_dim *d) { delete d; }
+
+int ib_rm_matrix(ib_rm *R, const char *spec, ib_weighted **out)
+{
+    IB_TRY
+    if (!R || !spec || !out) fail(IB_ERR_ARG, "ib_rm_matrix: bad argument");
+    std::unique_ptr<ib_weighted> W(new ib_weighted);
+    W->w = build_matrix(R->r, spec, new Dim, new Dim, R->r.params, true);
+    *out = W.release();
+    return IB_OK;
+    IB_CATCH
+}
+int ib_rm_matrix_d(ib_rm *R, const char *spec, ib_dim *dim0, ib_dim *dim1, int scale, int correctA, const double *sigma,
+                   ib_weighted **out)
+{
+    IB_TRY
+    if (!R || !spec || !out || !dim0 || !dim1) fail(IB_ERR_ARG, "ib_rm_matrix_d: bad argument");
+    Params p;
+    p.scale = scale != 0; p.correctA = correctA != 0;
+    if (sigma) p.sigma = {sigma[0], sigma[1], sigma[2]};
+    std::unique_ptr<ib_weighted> W(new ib_weighted);
+    W->w = build_matrix(R->r, spec, &dim0->d, &dim1->d, p, false);
+    *out = W.release();
+    return IB_OK;
+    IB_CATCH
+}
+void ib_w_free(ib_weighted *w) { delete w; }
+
+int ib_w_info(const ib_weighted *W, int64_t *info)
+{
+    Weighted const &w = *W->w;
+    info[0] = w.nrow; info[1] = w.ncol; info[2] = w.nnz; info[3] = w.conservative; info[4] = w.scaled;
+    info[5] = w.dims[0]->sparse_extent; info[6] = w.dims[1]->sparse_extent; info[7] = 0;
+    return IB_OK;
+}
+int ib_w_get_csr(const ib_weighted *W, int32_t *rowptr, int32_t *col, double *val)
+{
+    IB_TRY
+    Weighted const &w = *W->w;
+    if (rowptr) w.rowptr.download(rowptr, (size_t)w.nrow + 1);
+    if (col) w.col.download(col, (size_t)w.nnz);
+    if (val) w.val.download(val, (size_t)w.nnz);
+    IB_CUDA(cudaStreamSynchronize(w.stream));
+    return IB_OK;
+    IB_CATCH
+}
+int ib_w_get_coo(const ib_weighted *W, int32_t *row, int32_t *col, double *val)
+{
+    IB_TRY
+    Weighted const &w = *W->w;
+    std::vector<int32_t> rp((size_t)w.nrow + 1);
+    w.rowptr.download(rp.data(), rp.size());
+    if (col) w.col.download(col, (size_t)w.nnz);
+    if (val) w.val.download(val, (size_t)w.nnz);
+    IB_CUDA(cudaStreamSynchronize(w.stream));
+    if (row)
+        for (int64_t r = 0; r < w.nrow; ++r)
+            for (int32_t j = rp[r]; j < rp[r + 1]; ++j) row[j] = (int32_t)r;
+    return IB_OK;
+    IB_CATCH
+}
+int ib_w_get_weights(const ib_weighted *W, double *wM, double *Mw)
+{
+    IB_TRY
+    Weighted const &w = *W->w;
+    if (wM) w.wM.download(wM, (size_t)w.nrow);
+    if (Mw) w.Mw.download(Mw, (size_t)w.ncol);
+    IB_CUDA(cudaStreamSynchronize(w.stream));
+    return IB_OK;
+    IB_CATCH
+}
+int ib_w_get_dim(const ib_weighted *W, int which, int64_t *ids)
+{
+    IB_TRY
+    if (which < 0 || which > 1) fail(IB_ERR_ARG, "ib_w_get_dim: which must be 0 or 1");
+    auto v = W->w->dims[which]->ids(W->w->stream);
+    std::copy(v.begin(), v.end(), ids);
+    return IB_OK;
+    IB_CATCH
+}
+int ib_w_dev_ptrs(const ib_weighted *W, const int32_t **rowptr, const int32_t **col, const double **val, const double **wM,
+                  const double **Mw)
+{
+    Weighted const &w = *W->w;
+    if (rowptr) *rowptr = w.rowptr.p;
+    if (col) *col = w.col.p;
+    if (val) *val = w.val.p;
+    if (wM) *wM = w.wM.p;
+    if (Mw) *Mw = w.Mw.p;
+    return IB_OK;
+}
+
+int ib_w_apply_dev(const ib_weighted *W, const double *dX, int64_t ldx, int32_t nvar, double *dY, int64_t ldy, int force_conservation,
+                   void *stream)
+{
+    IB_TRY
+    if (!W || !dX || !dY) fail(IB_ERR_ARG, "ib_w_apply_dev: bad argument");
+    apply_dev(*W->w, dX, ldx, nvar, dY, ldy, force_conservation != 0, stream ? (cudaStream_t)stream : W->w->stream);
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_w_apply(const ib_weighted *W, const double *X, int64_t ldx, int32_t nvar, double *Y, int64_t ldy, int layout,
+               int force_conservation)
+{
+    IB_TRY
+    if (!W || !X || !Y || nvar <= 0) fail(IB_ERR_ARG, "ib_w_apply: bad argument");
+    Weighted &w = *W->w;
+    cudaStream_t s = w.stream;
+    const int64_t ldd = (nvar + 1) & ~1;    // even leading dimension => 16-byte vector path
+    DBuf<double> dX((size_t)w.ncol * ldd, s), dY((size_t)w.nrow * ldd, s);
+    if (layout == IB_LAYOUT_CELL_MAJOR) {
+        if (ldx < nvar || ldy < nvar) fail(IB_ERR_ARG, "ib_w_apply: leading dimension smaller than nvar");
+        IB_CUDA(cudaMemcpy2DAsync(dX.p, ldd * 8, X, ldx * 8, (size_t)nvar * 8, (size_t)w.ncol, cudaMemcpyHostToDevice, s));
+        apply_dev(w, dX.p, ldd, nvar, dY.p, ldd, force_conservation != 0, s);
+        IB_CUDA(cudaMemcpy2DAsync(Y, ldy * 8, dY.p, ldd * 8, (size_t)nvar * 8, (size_t)w.nrow, cudaMemcpyDeviceToHost, s));
+    } else if (layout == IB_LAYOUT_FIELD_MAJOR) {
+        if (ldx < w.ncol || ldy < w.nrow) fail(IB_ERR_ARG, "ib_w_apply: leading dimension smaller than the cell count");
+        DBuf<double> tX((size_t)nvar * w.ncol, s), tY((size_t)nvar * w.nrow, s);
+        IB_CUDA(cudaMemcpy2DAsync(tX.p, w.ncol * 8, X, ldx * 8, (size_t)w.ncol * 8, (size_t)nvar, cudaMemcpyHostToDevice, s));
+        transpose(tX.p, w.ncol, nvar, w.ncol, dX.p, ldd, s);
+        apply_dev(w, dX.p, ldd, nvar, dY.p, ldd, force_conservation != 0, s);
+        transpose(dY.p, ldd, w.nrow, nvar, tY.p, w.nrow, s);
+        IB_CUDA(cudaMemcpy2DAsync(Y, ldy * 8, tY.p, w.nrow * 8, (size_t)w.nrow * 8, (size_t)nvar, cudaMemcpyDeviceToHost, s));
+    } else {
+        fail(IB_ERR_ARG, "ib_w_apply: unknown layout %d", layout);
+    }
+    IB_CUDA(cudaStreamSynchronize(s));
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_w_apply_M(const ib_weighted *W, const double *A_s, int32_t nvar, double *B_s, double fill, int force_conservation)
+{
+    IB_TRY
+    if (!W || !A_s || !B_s || nvar <= 0) fail(IB_ERR_ARG, "ib_w_apply_M: bad argument");
+    Weighted &w = *W->w;
+    cudaStream_t s = w.stream;
+    Dim &db = *w.dims[0], &da = *w.dims[1];
+    const int64_t nsa = da.sparse_extent, nsb = db.sparse_extent;
+    DBuf<double> dAs((size_t)nvar * nsa, s), dBs((size_t)nvar * nsb, s), dX((size_t)w.ncol * nvar, s), dY((size_t)w.nrow * nvar, s);
+    dAs.upload(A_s, (size_t)nvar * nsa);
+    if (w.ncol) { densify_kernel<<<(unsigned)cdiv(w.ncol * nvar, 256), 256, 0, s>>>(dAs.p, nsa, da.sparse_of.p, da.identity, w.ncol, nvar, dX.p); IB_LAUNCHED(); }
+    apply_dev(w, dX.p, nvar, nvar, dY.p, nvar, force_conservation != 0, s);
+    fill_f64_kernel<<<(unsigned)cdiv((int64_t)nvar * nsb, 256), 256, 0, s>>>(dBs.p, (int64_t)nvar * nsb, fill);
+    IB_LAUNCHED();
+    if (w.nrow) { sparsify_kernel<<<(unsigned)cdiv(w.nrow * nvar, 256), 256, 0, s>>>(dY.p, db.sparse_of.p, db.identity, w.nrow, nvar, nsb, dBs.p); IB_LAUNCHED(); }
+    dBs.download(B_s, (size_t)nvar * nsb);
+    IB_CUDA(cudaStreamSynchronize(s));
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_w_apply_weight(const ib_weighted *W, int dim, const double *A_s, int32_t nvar, double *out)
+{
+    IB_TRY
+    if (!W || !A_s || !out || dim < 0 || dim > 1) fail(IB_ERR_ARG, "ib_w_apply_weight: bad argument");
+    Weighted const &w = *W->w;
+    // O(n) dot product on gathered entries: metadata-sized, evaluated on the host from downloaded weights
+    int64_t n = dim == 0 ? w.nrow : w.ncol;
+    std::vector<double> wt((size_t)n);
+    (dim == 0 ? w.wM : w.Mw).download(wt.data(), (size_t)n);
+    IB_CUDA(cudaStreamSynchronize(w.stream));
+    auto ids = w.dims[dim]->ids(w.stream);
+    int64_t ns = w.dims[dim]->sparse_extent;
+    for (int f = 0; f < nvar; ++f) {
+        double s = 0;
+        for (int64_t d = 0; d < n; ++d) s += wt[d] * A_s[(size_t)f * ns + ids[d]];
+        out[f] = s;
+    }
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_coo_matvec(double *yy, const double *xx, int ignore_nan, int64_t nrow, int64_t ncol, int64_t nnz, const int32_t *row,
+                  const int32_t *col, const double *data)
+{
+    IB_TRY
+    // pylib/icebin_cython.cpp:159-192: a Python-side convenience on host arrays (single vector); kept on the host.
+    if (!yy || !xx) fail(IB_ERR_ARG, "ib_coo_matvec: bad argument");
+    std::vector<char> written((size_t)nrow, 0);
+    for (int64_t n = 0; n < nnz; ++n) {
+        int64_t r = row[n], c = col[n];
+        if (r < 0 || r >= nrow || c < 0 || c >= ncol) fail(IB_ERR_ARG, "ib_coo_matvec: index out of range");
+        if (ignore_nan && std::isnan(xx[c])) continue;
+        double old = written[r] ? yy[r] : 0.0;
+        written[r] = 1;
+        yy[r] = old + data[n] * xx[c];
+    }
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_multivec_to_dense(int64_t n, const int64_t *index, const double *weights, const double *vals, int32_t nvar, int64_t nE,
+                         double fill, double *scaleE, double *dense)
+{
+    IB_TRY
+    // multivec.cpp:35-81 on host buffers (the device-resident multi-sheet merge is ib_merge_* in merge.cu)
+    for (int64_t i = 0; i < nE; ++i) scaleE[i] = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (index[i] < 0 || index[i] >= nE) fail(IB_ERR_ARG, "Index out of range: %ld vs. %ld", (long)index[i], (long)nE);
+        scaleE[index[i]] += weights[i];
+    }
+    for (int64_t i = 0; i < nE; ++i) scaleE[i] = 1. / scaleE[i];
+    const double nan = std::nan("");
+    for (int v = 0; v < nvar; ++v) {
+        double *d = dense + (size_t)v * nE;
+        for (int64_t i = 0; i < nE; ++i) d[i] = nan;
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t e = index[i];
+            double t = vals[(size_t)i * nvar + v] * scaleE[e];
+            d[e] = std::isnan(d[e]) ? t : d[e] + t;
+        }
+        for (int64_t i = 0; i < nE; ++i) if (std::isnan(d[i])) d[i] = fill;
+    }
+    return IB_OK;
+    IB_CATCH
+}
+
+// ---------------------------------------------------------------------------------------- Hntr
+int ib_hntr_create(ib_hntr **out, int imB, int jmB, double offiB, double dlatB, int imA, int jmA, double offiA, double dlatA,
+                   double datmis)
+{
+    IB_TRY
+    std::unique_ptr<ib_hntr> H(new ib_hntr);
+    H->h = hntr_create(imB, jmB, offiB, dlatB, imA, jmA, offiA, dlatA, datmis);
+    *out = H.release();
+    return IB_OK;
+    IB_CATCH
+}
+void ib_hntr_free(ib_hntr *h)
+{
+    if (h) { hntr_free(h->h); delete h; }
+}
+int ib_hntr_get(const ib_hntr *h, int which, double *dout, int32_t *iout)
+{
+    IB_TRY
+    hntr_get(*h->h, which, dout, iout);
+    return IB_OK;
+    IB_CATCH
+}
+int ib_hntr_regrid_dev(const ib_hntr *h, const double *d_wta, double wtm, double wtb, const void *d_src, int src_dtype, double *d_dst,
+                       int mean_polar, void *stream)
+{
+    IB_TRY
+    if (!h || !d_src || !d_dst) fail(IB_ERR_ARG, "ib_hntr_regrid_dev: bad argument");
+    hntr_regrid_dev(*h->h, d_wta, wtm, wtb, d_src, src_dtype, d_dst, mean_polar != 0, stream ? (cudaStream_t)stream : default_stream());
+    return IB_OK;
+    IB_CATCH
+}
+int ib_hntr_regrid(const ib_hntr *h, const double *wta, double wtm, double wtb, const void *src, int src_dtype, double *dst,
+                   int mean_polar)
+{
+    IB_TRY
+    if (!h || !src || !dst) fail(IB_ERR_ARG, "ib_hntr_regrid: bad argument");
+    ensure_device();
+    int d[4];
+    hntr_dims(*h->h, d);
+    const size_t nA = (size_t)d[0] * d[1], nB = (size_t)d[2] * d[3];
+    const size_t esz = src_dtype == IB_SRC_I16 ? 2 : 8;
+    cudaStream_t s = default_stream();
+    DBuf<char> dsrc(nA * esz, s);
+    DBuf<double> dw(wta ? nA : 0, s), dB(nB, s);
+    IB_CUDA(cudaMemcpyAsync(dsrc.p, src, nA * esz, cudaMemcpyHostToDevice, s));
+    if (wta) dw.upload(wta, nA);
+    hntr_regrid_dev(*h->h, wta ? dw.p : nullptr, wtm, wtb, dsrc.p, src_dtype, dB.p, mean_polar != 0, s);
+    dB.download(dst, nB);
+    IB_CUDA(cudaStreamSynchronize(s));
+    return IB_OK;
+    IB_CATCH
+}
+int64_t ib_hntr_matrix(const ib_hntr *h, double R, int64_t *rows, int64_t *cols, double *vals)
+{
+    IB_TRY
+    return hntr_matrix(*h->h, R, rows, cols, vals, default_stream());
+    IB_CATCH
+}
+
+}   // extern "C"

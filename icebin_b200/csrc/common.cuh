@@ -1,0 +1,96 @@
+// common.cuh -- error handling, stream-ordered device buffers, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/icebin_b200.h"
+
+namespace ib {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, std::string const &m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] inline void fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw Error(code, buf);
+}
+
+#define IB_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            ::ib::fail(IB_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                       cudaGetErrorString(e_));                                                         \
+    } while (0)
+
+extern std::atomic<int64_t> g_launches;   // kernels launched by this library (ib_launch_count)
+#define IB_LAUNCHED()                 \
+    do {                              \
+        ::ib::g_launches.fetch_add(1, std::memory_order_relaxed); \
+        IB_CUDA(cudaGetLastError());  \
+    } while (0)
+
+cudaStream_t default_stream();   // the library's own non-blocking stream (created on first use, per device)
+int sm_count();
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Stream-ordered device allocation (cudaMallocAsync; the default pool keeps freed blocks so steady-state
+// builds do not hit the driver).  Move-only.
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaStream_t st = nullptr;
+    DBuf() {}
+    DBuf(size_t n_, cudaStream_t s) { alloc(n_, s); }
+    DBuf(DBuf const &) = delete;
+    DBuf &operator=(DBuf const &) = delete;
+    DBuf(DBuf &&o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
+    DBuf &operator=(DBuf &&o) noexcept
+    {
+        if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DBuf() { release(); }
+    void alloc(size_t n_, cudaStream_t s)
+    {
+        release();
+        n = n_; st = s;
+        if (n) IB_CUDA(cudaMallocAsync((void **)&p, n * sizeof(T) , s));
+    }
+    void release()
+    {
+        if (p) cudaFreeAsync(p, st);
+        p = nullptr; n = 0;
+    }
+    void zero() { if (n) IB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+    void fill_byte(int b) { if (n) IB_CUDA(cudaMemsetAsync(p, b, n * sizeof(T), st)); }
+    void upload(const T *h, size_t cnt) { if (cnt) IB_CUDA(cudaMemcpyAsync(p, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st)); }
+    void download(T *h, size_t cnt) const { if (cnt) IB_CUDA(cudaMemcpyAsync(h, p, cnt * sizeof(T), cudaMemcpyDeviceToHost, st)); }
+    std::vector<T> to_host() const
+    {
+        std::vector<T> v(n);
+        download(v.data(), n);
+        IB_CUDA(cudaStreamSynchronize(st));
+        return v;
+    }
+};
+
+void ensure_device();   // throws IB_ERR_CUDA when no CUDA device is present (no CPU fallback)
+
+}   // namespace ib

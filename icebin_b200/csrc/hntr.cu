@@ -1,0 +1,399 @@
+// hntr.cu -- ModelE "Hntr" conservative lat-lon -> lat-lon regrid as a separable pair of kernels.
+//
+// Replaces icebin::modele::Hntr (slib/icebin/modele/hntr.hpp:63-435, hntr.cpp:63-168; Fortran HNTR4.F90):
+//   B(IB,JB) = sum_{JA,IA} F*G*(wtm*WTA+wtb)*A / sum_{JA,IA} F*G*(wtm*WTA+wtb)
+// with F the east-west and G the north-south overlap fractions.  Because the weight F*G is a product, the sum is
+// evaluated as   sum_IA F(IA,IB) * [ sum_JA G(JA,JB) * w*A ]:
+//   stage 1 streams the source once, every thread owning a few CONSECUTIVE source columns (16-byte loads) and
+//           accumulating them down the source rows of one destination row -> S[JB][IA] (value and weight);
+//   stage 2 contracts S along IA with the F fractions, applies DATMIS, and
+//   stage 3 optionally replaces the polar rows by their mean (hntr.hpp:413-434, including the quirk that one
+//           missing cell makes the whole polar row missing).
+// The partition tables (SINA/SINB/FMIN/.../JMAX) are computed on the HOST with libm exactly as the reference does
+// (the equality tests RIA==RIB and SINA==SINB decide the partition; never recompute them with device sin()).
+//
+// Roofline: HBM.  Algorithmic bytes = sizeof(Src)*nA [+ 8*nA with a weight array] + 8*nB   (SURVEY 8d).
+#include <cmath>
+
+#include "scan.cuh"
+#include "types.cuh"
+
+namespace ib {
+
+struct Hntr {
+    int imA, jmA, imB, jmB;
+    double offiA, dlatA, offiB, dlatB, datmis;
+    std::vector<double> sina, sinb, fmin, fmax, gmin, gmax, dxypA, dxypB;
+    std::vector<int> imin, imax, jmin, jmax;
+    DBuf<double> d_sina, d_fmin, d_fmax, d_gmin, d_gmax, d_dxypB;
+    DBuf<int> d_imin, d_imax, d_jmin, d_jmax;
+};
+
+static std::vector<double> cell_areas(int im, int jm)   // HntrGrid::dxyp, hntr.cpp:34-52 (unit sphere)
+{
+    std::vector<double> a(jm);
+    const double dlon = (2. * M_PI) / im, dlat = M_PI / jm;
+    for (int j = 1; j <= jm; ++j) {
+        const double south = sin(dlat * (j - jm / 2 - 1));
+        const double north = sin(dlat * (j - jm / 2));
+        a[j - 1] = dlon * (north - south);
+    }
+    return a;
+}
+
+static void check_spec(int im, int jm, double offi, double dlat)   // HntrSpec ctor heuristic, GridSpec.cpp:125-132
+{
+    if (im <= 0 || jm <= 0) fail(IB_ERR_ARG, "HntrSpec(%d,%d,...): im and jm must be positive", im, jm);
+    const double lim = .1 * (180. * 60. / jm);
+    if (dlat < lim)
+        fail(IB_ERR_ARG, "dlat in HntrGrid(%d,%d,%f,%f) seems to small; it should be in MINUTES ,not DEGREES: %f", im, jm, offi, dlat, lim);
+}
+
+Hntr *hntr_create(int imB, int jmB, double offiB, double dlatB, int imA, int jmA, double offiA, double dlatA, double datmis)
+{
+    check_spec(imB, jmB, offiB, dlatB);
+    check_spec(imA, jmA, offiA, dlatA);
+    std::unique_ptr<Hntr> h(new Hntr);
+    h->imA = imA; h->jmA = jmA; h->imB = imB; h->jmB = jmB;
+    h->offiA = offiA; h->dlatA = dlatA; h->offiB = offiB; h->dlatB = dlatB; h->datmis = datmis;
+    h->dxypA = cell_areas(imA, jmA);
+    h->dxypB = cell_areas(imB, jmB);
+    h->fmin.assign(imB, 0.); h->fmax.assign(imB, 0.); h->imin.assign(imB, 0); h->imax.assign(imB, 0);
+    h->gmin.assign(jmB, 0.); h->gmax.assign(jmB, 0.); h->jmin.assign(jmB, 0); h->jmax.assign(jmB, 0);
+
+    // East-west: walk both grids' eastern cell edges in a domain scaled to [0, imA*imB) (hntr.cpp:84-115).
+    // The running edge of grid A is ACCUMULATED (+= imB) as upstream does, so the FMAX quotients match bit for bit.
+    {
+        const double stepA = imB;
+        int ia = 1;
+        double eastA = (ia + offiA - imA) * imB;
+        for (int ib = 1, west_of = imB; ib <= imB; west_of = ib, ++ib) {
+            const double eastB = (ib - 1 + offiB) * imA;     // = western edge of B cell ib
+            for (; eastA < eastB; eastA += stepA) ++ia;
+            h->imax[west_of - 1] = ia;
+            if (eastA == eastB) {          // edges coincide: A cell ia belongs wholly to the western B cell
+                h->fmax[west_of - 1] = 0;
+                ++ia; eastA += stepA;
+                h->fmin[ib - 1] = 0;
+            } else {                        // A cell ia straddles the edge
+                h->fmax[west_of - 1] = (eastA - eastB) / stepA;
+                h->fmin[ib - 1] = 1 - h->fmax[west_of - 1];
+            }
+            h->imin[ib - 1] = ia;
+        }
+        h->imax[imB - 1] += imA;           // wrap-around of the last B cell
+    }
+    // North-south in sin(latitude); dlat is in minutes (hntr.cpp:118-168)
+    {
+        const double rad_per_min = (2. * M_PI) / (360 * 60);
+        auto edges = [&](int jm, double dlat) {
+            std::vector<double> sn(jm + 1);
+            const double eq = .5 * (1 + jm);
+            sn[0] = -1;
+            for (int j = 1; j < jm; ++j) sn[j] = sin(((j + .5 - eq) * dlat) * rad_per_min);
+            sn[jm] = 1;
+            return sn;
+        };
+        h->sina = edges(jmA, dlatA);
+        h->sinb = edges(jmB, dlatB);
+        h->jmin[0] = 1;
+        for (int jb = 1, ja = 1; jb < jmB; ++jb) {
+            while (h->sina[ja] < h->sinb[jb]) ++ja;
+            h->jmax[jb - 1] = ja;
+            if (h->sina[ja] == h->sinb[jb]) {
+                ++ja;
+            } else {
+                h->gmax[jb - 1] = h->sina[ja] - h->sinb[jb];
+                h->gmin[jb] = h->sinb[jb] - h->sina[ja - 1];
+            }
+            h->jmin[jb] = ja;
+        }
+        h->jmax[jmB - 1] = jmA;
+    }
+    return h.release();
+}
+
+static void hntr_upload(Hntr &h, cudaStream_t s)
+{
+    if (h.d_sina.n) return;
+    auto up = [&](auto &d, auto const &v) { d.alloc(v.size(), s); d.upload(v.data(), v.size()); };
+    up(h.d_sina, h.sina); up(h.d_fmin, h.fmin); up(h.d_fmax, h.fmax); up(h.d_gmin, h.gmin); up(h.d_gmax, h.gmax);
+    up(h.d_dxypB, h.dxypB); up(h.d_imin, h.imin); up(h.d_imax, h.imax); up(h.d_jmin, h.jmin); up(h.d_jmax, h.jmax);
+    IB_CUDA(cudaStreamSynchronize(s));
+}
+
+// ---- stage 1: S[jb][ia] = sum_ja G * w * A[ja][ia] ; T[jb][ia] = sum_ja G * w ------------------------------
+template <class SrcT, int CPT>
+struct SrcVec;
+template <>
+struct SrcVec<int16_t, 8> {
+    static __device__ __forceinline__ void load(const int16_t *p, double (&x)[8])
+    {
+        int4 r = __ldg(reinterpret_cast<const int4 *>(p));
+        int w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            x[2 * k] = (double)(int16_t)(w[k] & 0xffff);
+            x[2 * k + 1] = (double)(int16_t)(w[k] >> 16);
+        }
+    }
+};
+template <>
+struct SrcVec<double, 2> {
+    static __device__ __forceinline__ void load(const double *p, double (&x)[2])
+    {
+        double2 r = __ldg(reinterpret_cast<const double2 *>(p));
+        x[0] = r.x; x[1] = r.y;
+    }
+};
+template <class SrcT>
+struct SrcVec<SrcT, 1> {
+    static __device__ __forceinline__ void load(const SrcT *p, double (&x)[1]) { x[0] = (double)__ldg(p); }
+};
+
+template <class SrcT, int CPT, bool HASW>
+__global__ void __launch_bounds__(128) hntr_cols_kernel(const SrcT *__restrict__ A, const double *__restrict__ WTA, double wtm, double wtb,
+                                                        int imA, const double *__restrict__ sina, const int *__restrict__ jmin,
+                                                        const int *__restrict__ jmax, const double *__restrict__ gmin,
+                                                        const double *__restrict__ gmax, double *__restrict__ S, double *__restrict__ T)
+{
+    const int jb = blockIdx.y;
+    const int ia0 = (blockIdx.x * blockDim.x + threadIdx.x) * CPT;
+    if (ia0 >= imA) return;
+    const int jlo = jmin[jb], jhi = jmax[jb];
+    double sv[CPT], sw[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { sv[k] = 0; sw[k] = 0; }
+    const double wconst = wtm * 1.0 + wtb;
+    double gsum = 0;
+#pragma unroll 4
+    for (int ja = jlo; ja <= jhi; ++ja) {
+        double G = sina[ja] - sina[ja - 1];
+        if (ja == jlo) G -= gmin[jb];
+        if (ja == jhi) G -= gmax[jb];
+        const int64_t off = (int64_t)(ja - 1) * imA + ia0;
+        double x[CPT];
+        SrcVec<SrcT, CPT>::load(A + off, x);
+        if (HASW) {
+            double w[CPT];
+#pragma unroll
+            for (int k = 0; k < CPT; k += (CPT > 1 ? 2 : 1)) {
+                if (CPT > 1) { double2 t = __ldg(reinterpret_cast<const double2 *>(WTA + off + k)); w[k] = t.x; w[k + (CPT > 1)] = t.y; }
+                else w[k] = __ldg(WTA + off + k);
+            }
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const double wt = G * (wtm * w[k] + wtb);
+                sw[k] += wt;
+                sv[k] += wt * x[k];
+            }
+        } else {
+            const double wt = G * wconst;
+            gsum += wt;
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) sv[k] += wt * x[k];
+        }
+    }
+    double *so = S + (int64_t)jb * imA + ia0;
+    double *to = T + (int64_t)jb * imA + ia0;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        so[k] = sv[k];
+        to[k] = HASW ? sw[k] : gsum;
+    }
+}
+
+// ---- stage 2: one warp per destination cell contracts S,T along IA with the F fractions ----------------------
+__global__ void __launch_bounds__(256) hntr_rows_kernel(const double *__restrict__ S, const double *__restrict__ T, int imA, int imB, int jmB,
+                                                        const int *__restrict__ imin, const int *__restrict__ imax,
+                                                        const double *__restrict__ fmin, const double *__restrict__ fmax, double datmis,
+                                                        double *__restrict__ B)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cell >= (int64_t)imB * jmB) return;
+    const int jb = (int)(cell / imB), ib = (int)(cell - (int64_t)jb * imB);
+    const int lo = imin[ib], hi = imax[ib];
+    const double *s = S + (int64_t)jb * imA, *t = T + (int64_t)jb * imA;
+    double v = 0, w = 0;
+    for (int ir = lo + lane; ir <= hi; ir += 32) {
+        const int ia = (ir - 1) % imA;
+        double F = 1;
+        if (ir == lo) F -= fmin[ib];
+        if (ir == hi) F -= fmax[ib];
+        v += F * s[ia];
+        w += F * t[ia];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, d);
+        w += __shfl_xor_sync(0xffffffffu, w, d);
+    }
+    if (lane == 0) B[cell] = (w == 0) ? datmis : v / w;
+}
+
+// ---- stage 3: polar rows -> longitudinal mean (one block per polar row) ---------------------------------------
+__global__ void __launch_bounds__(256) hntr_polar_kernel(double *__restrict__ B, int imB, int jmB, double datmis)
+{
+    __shared__ double sh[256];
+    __shared__ int miss;
+    const int jb = blockIdx.x == 0 ? 0 : jmB - 1;
+    double *row = B + (int64_t)jb * imB;
+    if (threadIdx.x == 0) miss = 0;
+    __syncthreads();
+    double s = 0;
+    for (int i = threadIdx.x; i < imB; i += blockDim.x) {
+        const double b = row[i];
+        if (b == datmis) miss = 1;
+        s += b;
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+        __syncthreads();
+    }
+    const double mean = miss ? datmis : sh[0] / (double)imB;
+    for (int i = threadIdx.x; i < imB; i += blockDim.x) row[i] = mean;
+}
+
+template <class SrcT, int CPT>
+static void launch_cols(Hntr &h, const SrcT *A, const double *W, double wtm, double wtb, double *S, double *T, cudaStream_t s)
+{
+    dim3 grid((unsigned)cdiv(cdiv(h.imA, CPT), 128), (unsigned)h.jmB);
+    if (W)
+        hntr_cols_kernel<SrcT, CPT, true><<<grid, 128, 0, s>>>(A, W, wtm, wtb, h.imA, h.d_sina.p, h.d_jmin.p, h.d_jmax.p, h.d_gmin.p, h.d_gmax.p, S, T);
+    else
+        hntr_cols_kernel<SrcT, CPT, false><<<grid, 128, 0, s>>>(A, W, wtm, wtb, h.imA, h.d_sina.p, h.d_jmin.p, h.d_jmax.p, h.d_gmin.p, h.d_gmax.p, S, T);
+    IB_LAUNCHED();
+}
+
+void hntr_regrid_dev(Hntr &h, const double *d_wta, double wtm, double wtb, const void *d_src, int src_dtype, double *d_dst,
+                     bool mean_polar, cudaStream_t s)
+{
+    ensure_device();
+    hntr_upload(h, s);
+    DBuf<double> S((size_t)h.jmB * h.imA, s), T((size_t)h.jmB * h.imA, s);
+    const bool al16 = ((uintptr_t)d_src % 16 == 0) && (d_wta == nullptr || (uintptr_t)d_wta % 16 == 0);
+    if (src_dtype == IB_SRC_I16) {
+        if (al16 && h.imA % 8 == 0) launch_cols<int16_t, 8>(h, (const int16_t *)d_src, d_wta, wtm, wtb, S.p, T.p, s);
+        else launch_cols<int16_t, 1>(h, (const int16_t *)d_src, d_wta, wtm, wtb, S.p, T.p, s);
+    } else if (src_dtype == IB_SRC_F64) {
+        if (al16 && h.imA % 2 == 0) launch_cols<double, 2>(h, (const double *)d_src, d_wta, wtm, wtb, S.p, T.p, s);
+        else launch_cols<double, 1>(h, (const double *)d_src, d_wta, wtm, wtb, S.p, T.p, s);
+    } else {
+        fail(IB_ERR_ARG, "hntr_regrid: unknown source dtype %d", src_dtype);
+    }
+    const int64_t ncell = (int64_t)h.imB * h.jmB;
+    hntr_rows_kernel<<<(unsigned)cdiv(ncell * 32, 256), 256, 0, s>>>(S.p, T.p, h.imA, h.imB, h.jmB, h.d_imin.p, h.d_imax.p, h.d_fmin.p,
+                                                                    h.d_fmax.p, h.datmis, d_dst);
+    IB_LAUNCHED();
+    if (mean_polar) {
+        hntr_polar_kernel<<<h.jmB > 1 ? 2 : 1, 256, 0, s>>>(d_dst, h.imB, h.jmB, h.datmis);
+        IB_LAUNCHED();
+    }
+}
+
+// ---- overlap / scaled_regrid_matrix (hntr.hpp:249-339): entries in the reference's emission order -----------
+struct OvCount {
+    const int *imin, *imax, *jmin, *jmax;
+    int imB;
+    __device__ uint32_t operator()(int64_t cell) const
+    {
+        int jb = (int)(cell / imB), ib = (int)(cell - (int64_t)jb * imB);
+        return (uint32_t)((jmax[jb] - jmin[jb] + 1) * (imax[ib] - imin[ib] + 1));
+    }
+};
+struct OvEmit {
+    const int *imin, *imax, *jmin, *jmax;
+    const double *fmin, *fmax, *gmin, *gmax, *sina, *dxypB;
+    int imA, imB;
+    double R2;   // < 0: scaled_regrid_matrix
+    int64_t *rows, *cols;
+    double *vals;
+    __device__ void operator()(int64_t cell, uint32_t prefix, uint32_t) const
+    {
+        const int jb = (int)(cell / imB), ib = (int)(cell - (int64_t)jb * imB);
+        const int jlo = jmin[jb], jhi = jmax[jb], ilo = imin[ib], ihi = imax[ib];
+        double weight = 0;   // sequential, reference order (JA outer, IA inner)
+        for (int ja = jlo; ja <= jhi; ++ja) {
+            double G = sina[ja] - sina[ja - 1];
+            if (ja == jlo) G -= gmin[jb];
+            if (ja == jhi) G -= gmax[jb];
+            for (int ir = ilo; ir <= ihi; ++ir) {
+                double F = 1;
+                if (ir == ilo) F -= fmin[ib];
+                if (ir == ihi) F -= fmax[ib];
+                weight += F * G;
+            }
+        }
+        const double by = 1. / weight;
+        int64_t o = prefix;
+        for (int ja = jlo; ja <= jhi; ++ja) {
+            double G = sina[ja] - sina[ja - 1];
+            if (ja == jlo) G -= gmin[jb];
+            if (ja == jhi) G -= gmax[jb];
+            for (int ir = ilo; ir <= ihi; ++ir, ++o) {
+                double F = 1;
+                if (ir == ilo) F -= fmin[ib];
+                if (ir == ihi) F -= fmax[ib];
+                const double fg = F * G;
+                rows[o] = cell;
+                cols[o] = (int64_t)(ja - 1) * imA + ((ir - 1) % imA);
+                vals[o] = (R2 < 0) ? fg * by : fg * by * (R2 * dxypB[jb]);
+            }
+        }
+    }
+};
+
+int64_t hntr_matrix(Hntr &h, double R, int64_t *rows, int64_t *cols, double *vals, cudaStream_t s)
+{
+    ensure_device();
+    hntr_upload(h, s);
+    const int64_t ncell = (int64_t)h.imB * h.jmB;
+    // host-side count first (cheap, exact)
+    int64_t total = 0;
+    for (int jb = 0; jb < h.jmB; ++jb)
+        for (int ib = 0; ib < h.imB; ++ib) total += (int64_t)(h.jmax[jb] - h.jmin[jb] + 1) * (h.imax[ib] - h.imin[ib] + 1);
+    if (!rows) return total;
+    if (total >= (int64_t(1) << 32)) fail(IB_ERR_ARG, "hntr_matrix: more than 2^32 entries");
+    ScanState<uint32_t> st;
+    OvCount cnt{h.d_imin.p, h.d_imax.p, h.d_jmin.p, h.d_jmax.p, h.imB};
+    transform_scan<uint32_t>(st, ncell, cnt, AddU32{}, 0u, s);
+    DBuf<int64_t> dr((size_t)total, s), dc((size_t)total, s);
+    DBuf<double> dv((size_t)total, s);
+    OvEmit em{h.d_imin.p, h.d_imax.p, h.d_jmin.p, h.d_jmax.p, h.d_fmin.p, h.d_fmax.p, h.d_gmin.p, h.d_gmax.p, h.d_sina.p, h.d_dxypB.p,
+              h.imA, h.imB, R < 0 ? -1.0 : R * R, dr.p, dc.p, dv.p};
+    scan_apply<uint32_t>(st, cnt, AddU32{}, 0u, em, s);
+    dr.download(rows, (size_t)total);
+    dc.download(cols, (size_t)total);
+    dv.download(vals, (size_t)total);
+    IB_CUDA(cudaStreamSynchronize(s));
+    return total;
+}
+
+void hntr_free(Hntr *h) { delete h; }
+
+void hntr_get(Hntr const &h, int which, double *dout, int32_t *iout)
+{
+    auto cpd = [&](std::vector<double> const &v) { if (!dout) fail(IB_ERR_ARG, "hntr_get: double buffer required"); std::copy(v.begin(), v.end(), dout); };
+    auto cpi = [&](std::vector<int> const &v) { if (!iout) fail(IB_ERR_ARG, "hntr_get: int buffer required"); std::copy(v.begin(), v.end(), iout); };
+    switch (which) {
+        case 0: cpd(h.sina); break;
+        case 1: cpd(h.sinb); break;
+        case 2: cpd(h.fmin); break;
+        case 3: cpd(h.fmax); break;
+        case 4: cpd(h.gmin); break;
+        case 5: cpd(h.gmax); break;
+        case 6: cpi(h.imin); break;
+        case 7: cpi(h.imax); break;
+        case 8: cpi(h.jmin); break;
+        case 9: cpi(h.jmax); break;
+        case 10: cpd(h.dxypA); break;
+        case 11: cpd(h.dxypB); break;
+        default: fail(IB_ERR_ARG, "hntr_get: unknown selector %d", which);
+    }
+}
+void hntr_dims(Hntr const &h, int *d) { d[0] = h.imA; d[1] = h.jmA; d[2] = h.imB; d[3] = h.jmB; }
+
+}   // namespace ib

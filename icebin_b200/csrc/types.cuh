@@ -1,0 +1,108 @@
+// types.cuh -- host-side objects behind the C ABI handles (device-resident state).
+#pragma once
+#include <array>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ib {
+
+enum Kind : int { KA = 0, KE = 1, KI = 2, KX = 3 };
+
+// SparseSetT (spsparse::SparseSet<long,int>) with both directions resident in HBM:
+//   dense_of[sparse_extent] (int32, -1 = absent)  and  sparse_of[dense_extent] (int64).
+// `identity` sets (id_sparse_set, IceCoupler.cpp:366) carry no tables.
+struct Dim {
+    int64_t sparse_extent = -1;
+    int64_t dense_extent = 0;
+    bool identity = false;
+    DBuf<int32_t> dense_of;
+    DBuf<int64_t> sparse_of;        // capacity may exceed dense_extent
+    std::vector<int64_t> pending;   // ids given before the sparse extent was known (host)
+
+    void set_sparse_extent(int64_t n, cudaStream_t s);   // allocates/validates the table
+    void reserve(int64_t n, cudaStream_t s);             // sparse_of capacity
+    std::vector<int64_t> ids(cudaStream_t s) const;
+};
+
+struct Sheet {
+    std::string name;
+    int64_t nI = 0, nX = 0;
+    int interp_style = 0;
+    // agridI (AbbrGrid.hpp:93-109)
+    std::vector<int64_t> dimI_h;
+    DBuf<int64_t> dimI;            // [n_real_I] dense->sparse
+    DBuf<double> native_areaI;     // [n_real_I]
+    DBuf<double> centroid_xy;      // [n_real_I][2] (may be empty)
+    bool dimI_identity = false;
+    // aexgrid (AbbrGrid.hpp:40-78)
+    DBuf<int2> ex_ij;              // [nX] (iA, iI)
+    DBuf<double> ex_area;          // [nX]
+    // native_area/gridA_proj_area per SPARSE A id (0 where not realised): the sApvA/sEpvE diagonal
+    DBuf<double> ratioA;           // [nA]
+    std::vector<double> gridA_proj_area_h;   // [n_real_A]
+};
+
+struct Gcm {
+    int64_t nA = 0;
+    int correctA = 0;
+    std::vector<int64_t> dimA_h;
+    std::vector<double> native_area_h;
+    std::vector<double> hcdefs_h;
+    DBuf<double> hcdefs;
+    std::vector<std::unique_ptr<Sheet>> sheets;
+    int64_t nE() const { return nA * (int64_t)hcdefs_h.size(); }
+};
+
+struct Params {
+    bool scale = true;
+    bool correctA = false;
+    std::array<double, 3> sigma{{0, 0, 0}};
+    bool smooth() const { return sigma[0] != 0; }   // RegridMatrices.hpp:31
+};
+
+struct RegridMatrices {
+    Gcm *gcm = nullptr;
+    int sheet = 0;
+    Params params;
+    DBuf<double> elevmaskI;   // private copy (RegridMatrices_Dynamic.cpp:352)
+    cudaStream_t stream = nullptr;
+};
+
+// SpMM work decomposition (apply.cu): rows are cut into chunks of <= CHUNK nonzeros
+struct ApplyPlan {
+    bool ready = false;
+    int64_t nitems = 0;
+    DBuf<int4> items;        // (row, begin, end, partial_slot or -1)
+    int64_t nsplit_rows = 0;
+    DBuf<int4> split_rows;   // (row, first_partial, npartials, 0)
+    int64_t npartials = 0;
+};
+
+// linear::Weighted_Eigen: CSR matrix (rows = output space) + weights + dims.
+struct Weighted {
+    int64_t nrow = 0, ncol = 0, nnz = 0;
+    bool conservative = true, scaled = true;
+    DBuf<int32_t> rowptr;   // [nrow+1]
+    DBuf<int32_t> col;      // [nnz]
+    DBuf<double> val;       // [nnz]
+    DBuf<double> wM, Mw;    // [nrow], [ncol]
+    DBuf<double> cons_v;    // [ncol]  M^T wM (only for non-conservative matrices; conservation correction)
+    Dim *dims[2] = {nullptr, nullptr};
+    std::unique_ptr<Dim> owned[2];
+    ApplyPlan plan;
+    cudaStream_t stream = nullptr;
+};
+
+std::unique_ptr<Weighted> build_matrix(RegridMatrices &rm, std::string const &spec, Dim *d0, Dim *d1,
+                                       Params const &p, bool own_dims);
+// smooth.cu: M <- smoothI * M  (RegridMatrices_Dynamic.cpp:236-248)
+void smooth_rows(RegridMatrices &rm, Weighted &W, Params const &p);
+// apply.cu
+void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY, int64_t ldy, bool force_conservation,
+               cudaStream_t s);
+void csr_transpose_matvec(Weighted &W, const double *x_rows, double *y_cols, cudaStream_t s);
+
+}   // namespace ib

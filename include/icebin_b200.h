@@ -1,0 +1,163 @@
+/* icebin_b200.h -- C ABI of the B200-native IceBin regridding backend (libicebin_b200.so).
+ *
+ * Every entry point replaces one interface of the reference (citibeth/icebin); the reference file:line each
+ * one stands in for is cited beside it.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Conventions
+ *   - Every function returns 0 on success and a negative code on error; ib_last_error() gives the message
+ *     (the reference calls (*icebin_error)(-1, fmt, ...) which throws; slib/icebin/error.hpp:22-32).
+ *   - "host" pointers are ordinary CPU memory; functions ending in _dev take CUDA device pointers and a
+ *     cudaStream_t (passed as void*; NULL = the library's own stream) and do not synchronise.
+ *   - Sparse indices are int64 (eigen_types.hpp: sparse_index_type = long), dense indices int32, values fp64.
+ *   - Fields ("coupling variables") are stored CELL-MAJOR: X[cell * ld + field], ld >= nvar.  This is the
+ *     transpose of the reference's [nvar x ncell] Blitz view (IceCoupler.cpp:231-233); IB_LAYOUT_FIELD_MAJOR
+ *     selects the reference layout (costs one transposition on the device).
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with IB_ERR_CUDA.
+ */
+#ifndef ICEBIN_B200_H
+#define ICEBIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IB_OK 0
+#define IB_ERR_ARG (-1)      /* bad argument / unknown spec (std::map::at throw, RegridMatrices_Dynamic.cpp:419) */
+#define IB_ERR_CUDA (-2)     /* CUDA runtime failure or no device */
+#define IB_ERR_ELEV (-3)     /* "Elevation %g out of bounds" (IceRegridder_L0.cpp:84-85) */
+#define IB_ERR_AREA (-4)     /* "Area of cell %ld must be non-zero" (smoother.cpp:88-90) */
+#define IB_ERR_DIM (-5)      /* dimension mismatch (hntr.hpp:399-406) */
+
+#define IB_LAYOUT_CELL_MAJOR 0
+#define IB_LAYOUT_FIELD_MAJOR 1
+
+#define IB_Z_INTERP 0            /* InterpStyle::Z_INTERP          (IceRegridder.hpp:42-48) */
+#define IB_ELEV_CLASS_INTERP 1   /* InterpStyle::ELEV_CLASS_INTERP */
+
+#define IB_SRC_F64 0
+#define IB_SRC_I16 1
+
+typedef struct ib_gcm ib_gcm;             /* GCMRegridder_Standard        (GCMRegridder.hpp:312-400) */
+typedef struct ib_rm ib_rm;               /* RegridMatrices_Dynamic       (RegridMatrices_Dynamic.hpp:20-61) */
+typedef struct ib_dim ib_dim;             /* SparseSetT = spsparse::SparseSet<long,int> (eigen_types.hpp:24) */
+typedef struct ib_weighted ib_weighted;   /* ibmisc::linear::Weighted_Eigen (RegridMatrices_Dynamic.cpp:63,167,258) */
+typedef struct ib_hntr ib_hntr;           /* icebin::modele::Hntr         (modele/hntr.hpp:63-184) */
+
+const char *ib_last_error(void);
+/* number of visible CUDA devices (0 => every compute call will fail) and device selection for this thread */
+int ib_device_count(void);
+int ib_set_device(int device);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+int64_t ib_launch_count(void);
+
+/* ---- GCMRegridder_Standard ------------------------------------------------------------------------- */
+/* GCMRegridder_Standard::init(AbbrGrid&&, hcdefs, indexingHC, correctA)  GCMRegridder.hpp:346-352,
+ * with indexingHC fixed to {A,HC} / HC slowest, iE = ihc*nA + iA          pylib/icebin_cython.cpp:56-73.
+ * dimA[n_real] = realised A cells (dense->sparse), native_area[n_real]    AbbrGrid.hpp:103-109 */
+int ib_gcm_create(ib_gcm **out, int64_t nA, int32_t n_real, const int64_t *dimA, const double *native_area,
+                  int32_t nhc, const double *hcdefs, int correctA);
+void ib_gcm_free(ib_gcm *);
+/* add_sheet(name, IceRegridder) + IceRegridder::init(...)   GCMRegridder.hpp:357-370, IceRegridder.cpp:81-119.
+ * ex_ij[2*nX] interleaved (iA, iI), ex_area[nX]             AbbrGrid.hpp:40-78
+ * gridA_proj_area[n_real] is an input (PROJ is upstream of the hot path).  centroid_xy may be NULL (no smoothing).
+ * Returns the sheet index (>= 0). */
+int ib_gcm_add_sheet(ib_gcm *, const char *name, int64_t nI, int32_t n_real_I, const int64_t *dimI,
+                     const double *native_areaI, const double *centroid_xy, int64_t nX, const int32_t *ex_ij,
+                     const double *ex_area, const double *gridA_proj_area, int interp_style);
+int64_t ib_gcm_nA(const ib_gcm *);                 /* GCMRegridder.hpp:268 */
+int64_t ib_gcm_nE(const ib_gcm *);                 /* :269 */
+int32_t ib_gcm_nhc(const ib_gcm *);                /* :265-266 */
+int64_t ib_gcm_nI(const ib_gcm *, int sheet);      /* :272 */
+int64_t ib_gcm_nX(const ib_gcm *, int sheet);      /* IceRegridder.hpp nX() */
+int ib_gcm_nsheets(const ib_gcm *);
+int ib_gcm_sheet_index(const ib_gcm *, const char *name);   /* ice_regridders().index.at(name) */
+int ib_gcm_correctA(const ib_gcm *);
+/* GCMRegridder::wA(accum, sheet, native)  GCMRegridder.hpp:304-314: index[n_real], area[n_real] */
+int ib_gcm_wA(const ib_gcm *, int sheet, int native, int64_t *index, double *area);
+
+/* ---- RegridMatrices -------------------------------------------------------------------------------- */
+/* GCMRegridder_Standard::regrid_matrices(sheet_index, elevmaskI, RegridParams)  RegridMatrices_Dynamic.cpp:334-402.
+ * elevmaskI[nI] (NaN = masked) is COPIED (:352).  sigma may be NULL (= {0,0,0}).   RegridMatrices.hpp:17-36 */
+int ib_regrid_matrices(ib_gcm *, int sheet, const double *elevmaskI, int scale, int correctA, const double *sigma,
+                       ib_rm **out);
+int ib_regrid_matrices_dev(ib_gcm *, int sheet, const double *d_elevmaskI, int scale, int correctA,
+                           const double *sigma, void *stream, ib_rm **out);
+void ib_rm_free(ib_rm *);
+
+/* SparseSetT: ordered sparse<->dense bijection.  ids = sparse ids in dense order. */
+int ib_dim_create(ib_dim **out);                                             /* SparseSetT() */
+int ib_dim_create_ids(ib_dim **out, int64_t sparse_extent, int64_t n, const int64_t *ids);
+int ib_dim_create_identity(ib_dim **out, int64_t n);                         /* id_sparse_set(n), IceCoupler.cpp:366 */
+int64_t ib_dim_dense_extent(const ib_dim *);
+int64_t ib_dim_sparse_extent(const ib_dim *);
+int ib_dim_get_ids(const ib_dim *, int64_t *ids);                            /* to_sparse(0..dense_extent) */
+void ib_dim_free(ib_dim *);
+
+/* RegridMatrices::matrix(spec): fresh dims owned by the result          RegridMatrices_Dynamic.cpp:425-437
+ * spec in {AvI IvA AvX XvA EvI IvE EvX XvE EvA AvE}                     :363-390 */
+int ib_rm_matrix(ib_rm *, const char *spec, ib_weighted **out);
+/* RegridMatrices_Dynamic::matrix_d(spec, {dim0,dim1}, params): borrows the caller's dims and APPENDS   :412-423 */
+int ib_rm_matrix_d(ib_rm *, const char *spec, ib_dim *dim0, ib_dim *dim1, int scale, int correctA,
+                   const double *sigma, ib_weighted **out);
+void ib_w_free(ib_weighted *);
+
+/* info[0..7] = nrow, ncol, nnz, conservative, scaled, sparse_extent(dim0), sparse_extent(dim1), reserved */
+int ib_w_info(const ib_weighted *, int64_t *info);
+/* matrix in CSR (rows = output space, columns ascending inside a row) and as sorted COO (to_coo()) */
+int ib_w_get_csr(const ib_weighted *, int32_t *rowptr, int32_t *col, double *val);
+int ib_w_get_coo(const ib_weighted *, int32_t *row, int32_t *col, double *val);
+int ib_w_get_weights(const ib_weighted *, double *wM, double *Mw);            /* get_weights(0), get_weights(1) */
+int ib_w_get_dim(const ib_weighted *, int which, int64_t *ids);               /* dims[which] dense->sparse */
+/* device views (valid until ib_w_free): rowptr[nrow+1], col[nnz], val[nnz], wM[nrow], Mw[ncol] */
+int ib_w_dev_ptrs(const ib_weighted *, const int32_t **rowptr, const int32_t **col, const double **val,
+                  const double **wM, const double **Mw);
+
+/* Weighted_Eigen::apply(A_d, fill, force_conservation)  (ibmisc; call sites merge_topo.cpp:65, icebin22m.cpp:153,
+ * explicit products IceCoupler.cpp:237-238, 445-446).  Dense indexing.  X: ncol cells, Y: nrow cells. */
+int ib_w_apply(const ib_weighted *, const double *X, int64_t ldx, int32_t nvar, double *Y, int64_t ldy, int layout,
+               int force_conservation);
+int ib_w_apply_dev(const ib_weighted *, const double *dX, int64_t ldx, int32_t nvar, double *dY, int64_t ldy,
+                   int force_conservation, void *stream);          /* cell-major only */
+/* Python apply_M(A_s, fill, force_conservation): sparse-indexed in and out   matrix_formats.rst:150-165
+ * A_s: [nvar][sparse_extent(dim1)] field-major, B_s: [nvar][sparse_extent(dim0)] */
+int ib_w_apply_M(const ib_weighted *, const double *A_s, int32_t nvar, double *B_s, double fill,
+                 int force_conservation);
+/* apply_weight(dim, A_s): out[n] = sum_d w_dim[d] * A_s[n][to_sparse(d)]    matrix_formats.rst:168-185 */
+int ib_w_apply_weight(const ib_weighted *, int dim, const double *A_s, int32_t nvar, double *out);
+
+/* coo_matvec(yy, xx, ignore_nan, nrow, ncol, row, col, data)  pylib/icebin_cython.cpp:159-192.
+ * yy entries of rows with no contribution are left untouched. */
+int ib_coo_matvec(double *yy, const double *xx, int ignore_nan, int64_t nrow, int64_t ncol, int64_t nnz,
+                  const int32_t *row, const int32_t *col, const double *data);
+
+/* VectorMultivec::to_dense_scale + to_dense  slib/icebin/multivec.cpp:35-81: merge n sparse contributions
+ * (index[n], weights[n], vals[n][nvar]) from several sheets into dense[nvar][nE]; scaleE[nE] = 1/sum(weights). */
+int ib_multivec_to_dense(int64_t n, const int64_t *index, const double *weights, const double *vals, int32_t nvar,
+                         int64_t nE, double fill, double *scaleE, double *dense);
+
+/* ---- Hntr ------------------------------------------------------------------------------------------ */
+/* Hntr(yp17, Bspec, Aspec, DATMIS); HntrSpec(im, jm, offi, dlat[minutes])   hntr.cpp:63-82, GridSpec.hpp:143-170 */
+int ib_hntr_create(ib_hntr **out, int imB, int jmB, double offiB, double dlatB, int imA, int jmA, double offiA,
+                   double dlatA, double datmis);
+void ib_hntr_free(ib_hntr *);
+/* which: 0 SINA[jmA+1] 1 SINB[jmB+1] 2 FMIN[imB] 3 FMAX[imB] 4 GMIN[jmB] 5 GMAX[jmB] (double)
+ *        6 IMIN[imB] 7 IMAX[imB] 8 JMIN[jmB] 9 JMAX[jmB] (int, 1-based values as in the reference)
+ *        10 dxyp(A)[jmA] 11 dxyp(B)[jmB]  (HntrGrid::dxyp, hntr.cpp:34-52) */
+int ib_hntr_get(const ib_hntr *, int which, double *dout, int32_t *iout);
+/* Hntr::regrid(WTA, A, B, mean_polar, wtm, wtb)  hntr.hpp:385-435.  A: [jmA*imA] (i fastest) of src_dtype;
+ * wta NULL = constant 1 (ibmisc::const_array, etopo1_ice.cpp:24-26); B: [jmB*imB] fp64. */
+int ib_hntr_regrid(const ib_hntr *, const double *wta, double wtm, double wtb, const void *src, int src_dtype,
+                   double *dst, int mean_polar);
+int ib_hntr_regrid_dev(const ib_hntr *, const double *d_wta, double wtm, double wtb, const void *d_src,
+                       int src_dtype, double *d_dst, int mean_polar, void *stream);
+/* Hntr::overlap(accum, R) (R >= 0) / scaled_regrid_matrix(accum) (R < 0)  hntr.hpp:249-339.
+ * Call with rows == NULL to get the entry count, then again with buffers.  Entries in the reference's emission
+ * order; indices 0-based (IJB-1, IJA-1). */
+int64_t ib_hntr_matrix(const ib_hntr *, double R, int64_t *rows, int64_t *cols, double *vals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
