@@ -1,0 +1,81 @@
+"""GPU parity of the batched SpMM apply (K3) against the oracle's Eigen-order CSC x dense product."""
+import numpy as np
+import pytest
+
+from conftest import make_gpu, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_tol(Wo, X):
+    """|dY| <= 1e-12 * sum|terms|: scale for each output row."""
+    A = np.zeros(Wo.shape)
+    np.add.at(A, (Wo.row, Wo.col), np.abs(Wo.val))
+    return 1e-12 * (np.abs(X) @ A.T) + 1e-300
+
+
+@pytest.mark.parametrize("spec", ["EvI", "AvI", "IvE", "IvA", "EvA", "AvE"])
+@pytest.mark.parametrize("nvar", [1, 3, 26, 64])
+def test_apply_cfg1(cfg1, spec, nvar):
+    go, gg = make_oracle(cfg1), make_gpu(cfg1)
+    em = cfg1["elevmask"][0]
+    Wo = go.matrix(0, em, spec, scale=True, correctA=True)
+    Wg = gg.regrid_matrices(cfg1["sheets"][0].name, em, scale=True, correctA=True).matrix(spec)
+    X = np.random.default_rng(nvar).uniform(-1, 1, (nvar, Wo.shape[1]))
+    Yo = Wo.apply(X)
+    Yf = Wg.apply(X, layout="field")
+    Yc = Wg.apply(np.ascontiguousarray(X.T), layout="cell").T
+    assert np.array_equal(Yf, Yc)
+    assert np.all(np.abs(Yf - Yo) <= ref_tol(Wo, X))
+
+
+def test_apply_cfg2_bitexact_short_rows(cfg2):
+    """Rows with <= 32 nonzeros are accumulated in the oracle's order with mul-then-add: bit-identical."""
+    go, gg = make_oracle(cfg2), make_gpu(cfg2)
+    em = cfg2["elevmask"][0]
+    for spec in ("IvE", "IvA", "EvI", "AvI"):
+        Wo = go.matrix(0, em, spec, scale=True, correctA=True)
+        Wg = gg.regrid_matrices(cfg2["sheets"][0].name, em, scale=True, correctA=True).matrix(spec)
+        X = np.random.default_rng(7).uniform(-1, 1, (8, Wo.shape[1]))
+        Yo, Yg = Wo.apply(X), Wg.apply(X)
+        assert np.all(np.abs(Yg - Yo) <= ref_tol(Wo, X)), spec
+        rowlen = np.bincount(Wo.row, minlength=Wo.shape[0])
+        short = rowlen <= 32
+        assert np.array_equal(Yg[:, short], Yo[:, short]), spec
+        # conservation: sum wM * (M f) == sum Mw * f     (test_conserv.py:174-205)
+        lhs, rhs = (Yg * Wo.wM).sum(1), (X * Wo.Mw).sum(1)
+        scale = (np.abs(X) * Wo.Mw).sum(1)
+        assert np.all(np.abs(lhs - rhs) <= 1e-12 * scale), spec
+
+
+def test_apply_M_sparse_and_weights(cfg1):
+    go, gg = make_oracle(cfg1), make_gpu(cfg1)
+    sh = cfg1["sheets"][0]
+    em = cfg1["elevmask"][0]
+    Wg = gg.regrid_matrices(sh.name, em).matrix("AvI")
+    Wo = go.matrix(0, em, "AvI", scale=True, correctA=True)
+    f_s = np.random.default_rng(3).uniform(0, 1, (2, sh.nI))
+    B = Wg.apply_M(f_s, fill=-999.0)
+    assert B.shape == (2, gg.nA)
+    Yo = Wo.apply(f_s[:, Wo.dims[1]])
+    assert np.allclose(B[:, Wo.dims[0]], Yo, rtol=1e-12, atol=0)
+    untouched = np.ones(gg.nA, bool); untouched[Wo.dims[0]] = False
+    assert np.all(B[:, untouched] == -999.0)
+    assert np.allclose(Wg.apply_Mw(f_s), (f_s[:, Wo.dims[1]] * Wo.Mw).sum(1), rtol=1e-12)
+    assert np.allclose(Wg.apply_wM(B), (B[:, Wo.dims[0]] * Wo.wM).sum(1), rtol=1e-12)
+    coo = Wg.to_coo()
+    assert coo.shape == (gg.nA, sh.nI) and coo.nnz == Wo.nnz
+    one = Wg.apply_M(f_s[0])
+    assert one.shape == (gg.nA,) and np.isnan(one[untouched]).all()
+
+
+def test_constant_roundtrips(cfg2):
+    """tests/test_conserv/test_conserv.py:132-172: I->A->I, I->E->I, E->A->E, A->E->A of a constant return it."""
+    gg = make_gpu(cfg2)
+    rm = gg.regrid_matrices(cfg2["sheets"][0].name, cfg2["elevmask"][0], scale=True, correctA=False)
+    M = {s: rm.matrix(s) for s in ("AvI", "IvA", "EvI", "IvE", "EvA", "AvE")}
+    for a, b in (("AvI", "IvA"), ("EvI", "IvE"), ("AvE", "EvA"), ("EvA", "AvE")):
+        assert np.array_equal(M[a].dim(0), M[b].dim(1)) and np.array_equal(M[a].dim(1), M[b].dim(0))
+        one = np.ones((1, M[a].shape[1]))
+        back = M[b].apply(M[a].apply(one))
+        assert np.abs(back - 1).max() < 1e-13, (a, b)
