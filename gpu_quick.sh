@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests -x -q -m gpu 2>&1 | tail -30
+python bench.py --steps 500 --warmup 10 --no-cpu-baseline 2>&1 | tail -3
