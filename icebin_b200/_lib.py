@@ -44,6 +44,7 @@ SIGNATURES = {
     "ib_rm_matrix": (C.c_int, [vp, cp, PP]),
     "ib_rm_matrix_d": (C.c_int, [vp, cp, vp, vp, C.c_int, C.c_int, vp, PP]),
     "ib_w_free": (None, [vp]),
+    "ib_w_create_csr": (C.c_int, [PP, i64, i64, vp, vp, vp, vp, vp, C.c_int]),
     "ib_w_info": (C.c_int, [vp, vp]),
     "ib_w_get_csr": (C.c_int, [vp, vp, vp, vp]),
     "ib_w_get_coo": (C.c_int, [vp, vp, vp, vp]),

@@ -80,6 +80,16 @@ class Weighted:
         self.scaled = bool(info[4])
         self.sparse_extent = (int(info[5]), int(info[6]))
 
+    @classmethod
+    def from_csr(cls, nrow, ncol, rowptr, col, val, wM=None, Mw=None, conservative=True):
+        """Wrap a dense-indexed CSR matrix (extension; e.g. matrices read back from a Weighted_Eigen NetCDF dump)."""
+        rowptr = _c(rowptr, np.int32); col = _c(col, np.int32); val = _c(val, np.float64)
+        wM = None if wM is None else _c(wM, np.float64)
+        Mw = None if Mw is None else _c(Mw, np.float64)
+        h = vp()
+        check(lib().ib_w_create_csr(C.byref(h), nrow, ncol, _p(rowptr), _p(col), _p(val), _p(wM), _p(Mw), int(conservative)))
+        return cls(h)
+
     # ---- extraction
     def to_csr(self):
         rp = np.zeros(self.shape[0] + 1, np.int32)

@@ -1,47 +1,77 @@
 // apply.cu -- batched fp64 CSR SpMM  Y[nrow x nvar] = M * X[ncol x nvar]  with fields stored cell-major
-// (the nvar values of one cell are contiguous), so every nonzero drives one coalesced vector read of X.
+// (the nvar values of one cell are contiguous), so every nonzero drives one contiguous row read of X.
 //
 // Replaces ibmisc linear::Weighted_Eigen::apply()/apply_M() (call sites merge_topo.cpp:65, modele/icebin22m.cpp:153)
 // and the explicit Eigen products of the coupling step (IceCoupler.cpp:237-238, 445-446).
 //
-// Compiled with -fmad=false: a row is accumulated as acc = acc + v*x over ascending columns, which is exactly the
-// order and rounding of Eigen's column-major sparse * dense on the CPU, so rows that are not split agree with the
-// oracle bit for bit.  Rows longer than APPLY_CHUNK nonzeros are cut into chunks whose partial sums are added in
-// chunk order by a second kernel (deterministic; differs from the CPU order only in association).
+// Work decomposition ("items", built once per matrix on the device):
+//   * consecutive SHORT rows (<= APPLY_CHUNK nonzeros) are packed into groups of < 2*APPLY_CHUNK nonzeros and
+//     <= 32 rows, so that matrices with 2 nonzeros per row (IvE, IvA) move as much data per unit as long rows do;
+//   * LONG rows are cut into chunks of APPLY_CHUNK nonzeros whose partial sums are combined, in chunk order, by a
+//     small second kernel (a fused "last block adds" variant was measured 15-25 % slower: its fence + atomic round
+//     trip stalls the consumers of every chunk while the ring drains).
+// Main kernel (spmm_tma_kernel): one producer warp streams the X rows named by an item's column indices into a
+// shared-memory ring with 1-D bulk async copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers; eight
+// consumer warps read each landed row once (one double2 per thread) and keep running sums in registers.  Bytes in
+// flight per SM are set by the ring, not by registers.  A plain-load kernel (spmm_ldg_kernel) covers small or odd
+// nvar and unaligned buffers.
+//
+// Compiled with -fmad=false: a row is accumulated as acc = acc + v*x over ascending columns, exactly the order and
+// rounding of Eigen's column-major sparse * dense on the CPU, so rows of <= APPLY_CHUNK nonzeros agree with the
+// oracle bit for bit; split rows differ only in association.
 //
 // Roofline: HBM.  Algorithmic bytes = 12*nnz + 4*(nrow+1) + 8*nvar*(ncol_touched + nrow)   (SURVEY 8d).
+#include <cstdlib>
+
 #include "scan.cuh"
 #include "types.cuh"
 
 namespace ib {
 
 constexpr int APPLY_CHUNK = 32;
+constexpr int GROUP_ROWS = 32;
 
-// ---- plan: (row, begin, end, partial slot | -1) items ---------------------------------------------------
+// ---- plan -----------------------------------------------------------------------------------------------
+// item = (first_row, nnz_begin, nnz_end, w):  w >= 0: chunk of a long row, w = partial slot
+//                                             w <  0: group of -w consecutive short rows
 struct PlanLoad {
     const int32_t *rowptr;
+    __device__ __forceinline__ int len(int64_t r) const { return rowptr[r + 1] - rowptr[r]; }
+    __device__ __forceinline__ bool same_group(int64_t a, int64_t b) const   // a, b short rows, b = a + 1
+    {
+        return (rowptr[a] / APPLY_CHUNK == rowptr[b] / APPLY_CHUNK) && (a / GROUP_ROWS == b / GROUP_ROWS);
+    }
     __device__ uint4 operator()(int64_t r) const
     {
-        int len = rowptr[r + 1] - rowptr[r];
-        uint32_t nch = len <= APPLY_CHUNK ? 1u : (uint32_t)((len + APPLY_CHUNK - 1) / APPLY_CHUNK);
-        return make_uint4(nch, nch > 1 ? nch : 0u, nch > 1 ? 1u : 0u, 0u);
+        const int n = len(r);
+        if (n > APPLY_CHUNK) {
+            const uint32_t nch = (uint32_t)((n + APPLY_CHUNK - 1) / APPLY_CHUNK);
+            return make_uint4(nch, nch, 1u, 0u);
+        }
+        const bool head = (r == 0) || len(r - 1) > APPLY_CHUNK || !same_group(r - 1, r);
+        return make_uint4(head ? 1u : 0u, 0u, 0u, 0u);
     }
 };
 struct PlanApply {
-    const int32_t *rowptr;
+    PlanLoad L;
+    int64_t nrow;
     int4 *items;
-    int4 *split_rows;
+    int4 *split_rows;      // (row, first partial slot, nchunks, 0)
+    int32_t *slot_srow;    // partial slot -> split-row index
     __device__ void operator()(int64_t r, uint4 prefix, uint4 e) const
     {
-        int b = rowptr[r], end = rowptr[r + 1];
-        if (e.x == 1) {
-            items[prefix.x] = make_int4((int)r, b, end, -1);
-        } else {
+        const int b = L.rowptr[r], end = L.rowptr[r + 1];
+        if (e.z) {
             for (uint32_t q = 0; q < e.x; ++q) {
-                int lo = b + (int)q * APPLY_CHUNK;
+                const int lo = b + (int)q * APPLY_CHUNK;
                 items[prefix.x + q] = make_int4((int)r, lo, min(end, lo + APPLY_CHUNK), (int)(prefix.y + q));
+                slot_srow[prefix.y + q] = (int32_t)prefix.z;
             }
             split_rows[prefix.z] = make_int4((int)r, (int)prefix.y, (int)e.x, 0);
+        } else if (e.x) {
+            int64_t r2 = r + 1;
+            while (r2 < nrow && L.len(r2) <= APPLY_CHUNK && L.same_group(r2 - 1, r2)) ++r2;
+            items[prefix.x] = make_int4((int)r, b, L.rowptr[r2], -(int)(r2 - r));
         }
     }
 };
@@ -53,27 +83,167 @@ static void make_plan(Weighted &W, cudaStream_t s)
     if (W.nrow > 0) {
         ScanState<uint4> st;
         const uint4 z = make_uint4(0, 0, 0, 0);
-        transform_scan<uint4>(st, W.nrow, PlanLoad{W.rowptr.p}, AddU32x4{}, z, s);
+        PlanLoad L{W.rowptr.p};
+        transform_scan<uint4>(st, W.nrow, L, AddU32x4{}, z, s);
         uint4 tot;
         IB_CUDA(cudaMemcpyAsync(&tot, st.total.p, sizeof tot, cudaMemcpyDeviceToHost, s));
         IB_CUDA(cudaStreamSynchronize(s));
         P.nitems = tot.x; P.npartials = tot.y; P.nsplit_rows = tot.z;
         P.items.alloc((size_t)P.nitems, s);
         P.split_rows.alloc((size_t)P.nsplit_rows, s);
-        scan_apply<uint4>(st, PlanLoad{W.rowptr.p}, AddU32x4{}, z, PlanApply{W.rowptr.p, P.items.p, P.split_rows.p}, s);
+        P.slot_srow.alloc((size_t)P.npartials, s);
+        scan_apply<uint4>(st, L, AddU32x4{}, z, PlanApply{L, W.nrow, P.items.p, P.split_rows.p, P.slot_srow.p}, s);
     }
     P.ready = true;
 }
 
-// ---- main kernel ----------------------------------------------------------------------------------------
-// A group of L lanes (L = 1..32, power of two) owns one (item, field-tile) unit; lane fl of the group owns VEC
-// consecutive fields.  No cross-lane traffic: every lane walks the item's nonzeros and keeps its own sums.
+// ---- TMA (cp.async.bulk) pipeline -----------------------------------------------------------------------
+constexpr int TMA_ROWS = 4;          // X rows per pipeline stage (amortises the barrier round trip)
+constexpr int TMA_CONSUMERS = 256;   // consumer threads (8 warps); +1 producer warp
+constexpr int TMA_MAX_TW = 2 * TMA_CONSUMERS;   // fields per tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct SpmmArgs {
+    const int4 *items;
+    int64_t nunits;
+    int ntile, tw, nstage;
+    const int32_t *rowptr, *col;
+    const double *val, *X;
+    int64_t ldx;
+    int nvar;
+    double *Y;
+    int64_t ldy;
+    double *partials;
+    int64_t ldp;
+};
+
+__global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const SpmmArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + a.nstage;
+    unsigned char *data = smem_raw + 256;           // 2*nstage*8 <= 248
+    const uint32_t rowbytes = (uint32_t)a.tw * 8u;
+    const uint32_t stagebytes = rowbytes * TMA_ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, TMA_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int stage = 0;
+    uint32_t phase = 0;
+    if (warp == TMA_CONSUMERS / 32) {
+        // ===== producer warp: lanes 0..nr-1 each issue one row copy of the stage
+        for (int64_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+            const int64_t item = u / a.ntile;
+            const int tile = (int)(u - item * a.ntile);
+            const int4 it = a.items[item];
+            const int f0 = tile * a.tw;
+            const uint32_t tb = (uint32_t)min(a.tw, a.nvar - f0) * 8u;
+            for (int j = it.y; j < it.z; j += TMA_ROWS) {
+                const int nr = min(TMA_ROWS, it.z - j);
+                const int c = (lane < nr) ? __ldg(a.col + j + lane) : 0;
+                if (lane == 0) {
+                    mbar_wait(empty + stage, phase ^ 1u);
+                    mbar_expect_tx(full + stage, tb * (uint32_t)nr);
+                }
+                __syncwarp();
+                if (lane < nr)
+                    bulk_g2s(data + (size_t)stage * stagebytes + (size_t)lane * rowbytes, a.X + (int64_t)c * a.ldx + f0, tb, full + stage);
+                if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== consumer warps: thread t owns fields f0 + 2t, f0 + 2t + 1
+        const int t = threadIdx.x;
+        for (int64_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+            const int64_t item = u / a.ntile;
+            const int tile = (int)(u - item * a.ntile);
+            const int4 it = a.items[item];
+            const int f0 = tile * a.tw;
+            const bool active = 2 * t < min(a.tw, a.nvar - f0);
+            const int nrows = it.w < 0 ? -it.w : 0;
+            // row ends of a group live one per lane (nrows <= 32)
+            int my_end = (lane < nrows) ? __ldg(a.rowptr + it.x + lane + 1) : 0;
+            int cur = 0;
+            int cur_end = nrows ? __shfl_sync(0xffffffffu, my_end, 0) : it.z;
+            double a0 = 0.0, a1 = 0.0;
+            int j = it.y;
+            // leading empty rows of a group
+            while (cur < nrows && cur_end == j) {
+                if (active) reinterpret_cast<double2 *>(a.Y + (int64_t)(it.x + cur) * a.ldy + f0)[t] = make_double2(0.0, 0.0);
+                ++cur;
+                cur_end = __shfl_sync(0xffffffffu, my_end, cur & 31);
+            }
+            for (int jb = it.y; jb < it.z; jb += TMA_ROWS) {
+                const int nr = min(TMA_ROWS, it.z - jb);
+                double v[TMA_ROWS];
+#pragma unroll
+                for (int r = 0; r < TMA_ROWS; ++r) v[r] = (r < nr) ? __ldg(a.val + jb + r) : 0.0;
+                mbar_wait(full + stage, phase);
+                const unsigned char *sp = data + (size_t)stage * stagebytes + (size_t)t * 16;
+#pragma unroll
+                for (int r = 0; r < TMA_ROWS; ++r) {
+                    if (r < nr) {
+                        if (active) {
+                            const double2 x = *reinterpret_cast<const double2 *>(sp + (size_t)r * rowbytes);
+                            a0 = a0 + v[r] * x.x;
+                            a1 = a1 + v[r] * x.y;
+                        }
+                        ++j;
+                        while (cur < nrows && cur_end == j) {      // row(s) of a group complete
+                            if (active) reinterpret_cast<double2 *>(a.Y + (int64_t)(it.x + cur) * a.ldy + f0)[t] = make_double2(a0, a1);
+                            a0 = 0.0; a1 = 0.0;
+                            ++cur;
+                            cur_end = __shfl_sync(0xffffffffu, my_end, cur & 31);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);
+                if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
+            }
+            if (it.w >= 0 && active)   // chunk of a long row: partial sum, combined in chunk order by spmm_fixup_kernel
+                reinterpret_cast<double2 *>(a.partials + (int64_t)it.w * a.ldp + f0)[t] = make_double2(a0, a1);
+        }
+    }
+}
+
+// ---- plain-load fallback (small / odd nvar, unaligned buffers) ---------------------------------------------
+// A group of L lanes (power of two) owns one (item, field-tile) unit; lane fl owns VEC consecutive fields.
 template <int VEC>
-__global__ void __launch_bounds__(256) spmm_kernel(const int4 *__restrict__ items, int64_t nunits, int ntile, int L,
-                                                   const int32_t *__restrict__ col, const double *__restrict__ val,
-                                                   const double *__restrict__ X, int64_t ldx, int nvar,
-                                                   double *__restrict__ Y, int64_t ldy, double *__restrict__ partials,
-                                                   int64_t ldp, const double *__restrict__ factor)
+__global__ void __launch_bounds__(256) spmm_ldg_kernel(const int4 *__restrict__ items, int64_t nunits, int ntile, int L,
+                                                       const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                       const double *__restrict__ val, const double *__restrict__ X, int64_t ldx,
+                                                       int nvar, double *__restrict__ Y, int64_t ldy, double *__restrict__ partials,
+                                                       int64_t ldp)
 {
     const int lane = threadIdx.x & 31;
     const int G = 32 / L;
@@ -86,61 +256,80 @@ __global__ void __launch_bounds__(256) spmm_kernel(const int4 *__restrict__ item
         const int f0 = (tile * L + fl) * VEC;
         if (f0 >= nvar) continue;
         const int4 it = items[item];
-        double acc[VEC];
+        const int nrows = it.w < 0 ? -it.w : 1;
+        for (int rr = 0; rr < nrows; ++rr) {
+            const int jb = it.w < 0 ? __ldg(rowptr + it.x + rr) : it.y;
+            const int je = it.w < 0 ? __ldg(rowptr + it.x + rr + 1) : it.z;
+            double acc[VEC];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[k] = 0.0;
-        int j = it.y;
-        for (; j + 4 <= it.z; j += 4) {
-            int c[4];
-            double v[4];
-            double x[4][VEC];
+            for (int k = 0; k < VEC; ++k) acc[k] = 0.0;
+            int j = jb;
+            for (; j + 4 <= je; j += 4) {
+                int c[4];
+                double v[4];
+                double x[4][VEC];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { c[q] = __ldg(col + j + q); v[q] = __ldg(val + j + q); }
+                for (int q = 0; q < 4; ++q) { c[q] = __ldg(col + j + q); v[q] = __ldg(val + j + q); }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double *xp = X + (int64_t)c[q] * ldx + f0;
-                if (VEC == 2) { double2 t = __ldg(reinterpret_cast<const double2 *>(xp)); x[q][0] = t.x; x[q][VEC - 1] = t.y; }
-                else x[q][0] = __ldg(xp);
+                for (int q = 0; q < 4; ++q) {
+                    const double *xp = X + (int64_t)c[q] * ldx + f0;
+                    if (VEC == 2) { double2 tt = __ldg(reinterpret_cast<const double2 *>(xp)); x[q][0] = tt.x; x[q][VEC - 1] = tt.y; }
+                    else x[q][0] = __ldg(xp);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[k] = acc[k] + v[q] * x[q][k];
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) acc[k] = acc[k] + v[q] * x[q][k];
-        }
-        for (; j < it.z; ++j) {
-            const int c = __ldg(col + j);
-            const double v = __ldg(val + j);
-            const double *xp = X + (int64_t)c * ldx + f0;
-            if (VEC == 2) { double2 t = __ldg(reinterpret_cast<const double2 *>(xp)); acc[0] = acc[0] + v * t.x; acc[VEC - 1] = acc[VEC - 1] + v * t.y; }
-            else acc[0] = acc[0] + v * __ldg(xp);
-        }
-        double *out;
-        if (it.w < 0) {
-            out = Y + (int64_t)it.x * ldy + f0;
-            if (factor) {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) acc[k] = acc[k] * factor[f0 + k];
+            for (; j < je; ++j) {
+                const int c = __ldg(col + j);
+                const double v = __ldg(val + j);
+                const double *xp = X + (int64_t)c * ldx + f0;
+                if (VEC == 2) { double2 tt = __ldg(reinterpret_cast<const double2 *>(xp)); acc[0] = acc[0] + v * tt.x; acc[VEC - 1] = acc[VEC - 1] + v * tt.y; }
+                else acc[0] = acc[0] + v * __ldg(xp);
             }
-        } else {
-            out = partials + (int64_t)it.w * ldp + f0;
+            double *out = (it.w < 0) ? (Y + (int64_t)(it.x + rr) * ldy + f0) : (partials + (int64_t)it.w * ldp + f0);
+            if (VEC == 2) *reinterpret_cast<double2 *>(out) = make_double2(acc[0], acc[VEC - 1]);
+            else out[0] = acc[0];
         }
-        if (VEC == 2) *reinterpret_cast<double2 *>(out) = make_double2(acc[0], acc[VEC - 1]);
-        else out[0] = acc[0];
     }
 }
 
-__global__ void spmm_fixup_kernel(const int4 *__restrict__ split_rows, int64_t nsplit, const double *__restrict__ partials,
-                                  int64_t ldp, int nvar, double *__restrict__ Y, int64_t ldy, const double *__restrict__ factor)
+// Y[row] = sum of the row's chunk partials, added in chunk order (deterministic)
+template <int VEC>
+__global__ void __launch_bounds__(256) spmm_fixup_kernel(const int4 *__restrict__ split_rows, int64_t nsplit,
+                                                         const double *__restrict__ partials, int64_t ldp, int nvar,
+                                                         double *__restrict__ Y, int64_t ldy)
 {
+    const int nv = nvar / VEC;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t r = t / nvar;
-    int f = (int)(t - r * nvar);
+    int64_t r = t / nv;
+    int f = (int)(t - r * nv) * VEC;
     if (r >= nsplit) return;
-    int4 sr = split_rows[r];
-    double s = partials[(int64_t)sr.y * ldp + f];
-    for (int q = 1; q < sr.z; ++q) s = s + partials[(int64_t)(sr.y + q) * ldp + f];
-    if (factor) s = s * factor[f];
-    Y[(int64_t)sr.x * ldy + f] = s;
+    const int4 sr = split_rows[r];
+    const double *pp = partials + (int64_t)sr.y * ldp + f;
+    double s[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) s[k] = 0.0;   // 0 + p0 == p0 exactly
+    int q = 0;
+    for (; q + 4 <= sr.z; q += 4) {
+        double p[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (VEC == 2) { double2 tt = __ldcg(reinterpret_cast<const double2 *>(pp + (int64_t)(q + u) * ldp)); p[u][0] = tt.x; p[u][VEC - 1] = tt.y; }
+            else p[u][0] = __ldcg(pp + (int64_t)(q + u) * ldp);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) s[k] = s[k] + p[u][k];
+    }
+    for (; q < sr.z; ++q)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s[k] = s[k] + __ldcg(pp + (int64_t)q * ldp + k);
+    double *out = Y + (int64_t)sr.x * ldy + f;
+    if (VEC == 2) *reinterpret_cast<double2 *>(out) = make_double2(s[0], s[VEC - 1]);
+    else out[0] = s[0];
 }
 
 // ---- conservation correction (ibmisc Weighted_Eigen::apply_e; matrix_formats.rst:156-165) ---------------
@@ -192,27 +381,61 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
     make_plan(W, s);
     ApplyPlan &P = W.plan;
     const bool vec2 = (nvar % 2 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && ((uintptr_t)dX % 16 == 0) && ((uintptr_t)dY % 16 == 0);
-    const int VEC = vec2 ? 2 : 1;
-    const int lanes_needed = (nvar + VEC - 1) / VEC;
-    int L = 1;
-    while (L < 32 && L < lanes_needed) L <<= 1;
-    const int ntile = (lanes_needed + L - 1) / L;
-    const int64_t nunits = P.nitems * ntile;
     const int64_t ldp = (nvar + 1) & ~1;
     DBuf<double> partials((size_t)P.npartials * ldp, s);
 
-    const int G = 32 / L;
-    int64_t warps_needed = cdiv(nunits, G);
-    int64_t blocks = std::min<int64_t>(cdiv(warps_needed, 8), (int64_t)sm_count() * 8);
-    if (blocks < 1) blocks = 1;
-    if (VEC == 2)
-        spmm_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp, nullptr);
-    else
-        spmm_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp, nullptr);
-    IB_LAUNCHED();
+    static const int variant = getenv("IB_SPMM_VARIANT") ? atoi(getenv("IB_SPMM_VARIANT")) : 0;   // 0 auto, 1 LDG, 2 TMA
+    static const int want_bps = getenv("IB_SPMM_BPS") ? atoi(getenv("IB_SPMM_BPS")) : 4;            // TMA blocks per SM
+    bool done = false;
+    if (vec2 && nvar >= 64 && variant != 1) {
+        const int tw = std::min(nvar, TMA_MAX_TW);
+        const int ntile = (nvar + tw - 1) / tw;
+        const int64_t nunits = P.nitems * ntile;
+        static int max_smem = 0;
+        if (!max_smem) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            IB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        }
+        const size_t stagebytes = (size_t)tw * 8 * TMA_ROWS;
+        const size_t budget = (size_t)(max_smem + 1024) / want_bps - 1024 - 256;
+        const int nstage = (int)std::min<size_t>(15, budget / stagebytes);
+        if (nstage >= 2) {
+            const size_t smem = 256 + (size_t)nstage * stagebytes;
+            const int64_t slots = (int64_t)sm_count() * want_bps;
+            const int64_t per = std::max<int64_t>(1, cdiv(nunits, slots));
+            const int64_t nblk = std::max<int64_t>(1, cdiv(nunits, per));
+            SpmmArgs a{P.items.p, nunits, ntile, tw, nstage, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp};
+            spmm_tma_kernel<<<(unsigned)nblk, TMA_CONSUMERS + 32, smem, s>>>(a);
+            IB_LAUNCHED();
+            done = true;
+        }
+    }
+    if (!done) {
+        const int VEC = vec2 ? 2 : 1;
+        const int lanes_needed = (nvar + VEC - 1) / VEC;
+        int L = 1;
+        while (L < 32 && L < lanes_needed) L <<= 1;
+        const int ntile = (lanes_needed + L - 1) / L;
+        const int64_t nunits = P.nitems * ntile;
+        const int G = 32 / L;
+        int64_t blocks = std::min<int64_t>(cdiv(cdiv(nunits, G), 8), (int64_t)sm_count() * 8);
+        if (blocks < 1) blocks = 1;
+        if (VEC == 2)
+            spmm_ldg_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp);
+        else
+            spmm_ldg_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp);
+        IB_LAUNCHED();
+    }
     if (P.nsplit_rows > 0) {
-        int64_t tot = P.nsplit_rows * nvar;
-        spmm_fixup_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, s>>>(P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy, nullptr);
+        if (vec2) {
+            int64_t tot = P.nsplit_rows * (nvar / 2);
+            spmm_fixup_kernel<2><<<(unsigned)cdiv(tot, 256), 256, 0, s>>>(P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy);
+        } else {
+            int64_t tot = P.nsplit_rows * (int64_t)nvar;
+            spmm_fixup_kernel<1><<<(unsigned)cdiv(tot, 256), 256, 0, s>>>(P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy);
+        }
         IB_LAUNCHED();
     }
     if (!W.conservative && force_conservation) {

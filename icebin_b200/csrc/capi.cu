@@ -340,6 +340,39 @@ int ib_rm_matrix_d(ib_rm *R, const char *spec, ib_dim *dim0, ib_dim *dim1, int s
 }
 void ib_w_free(ib_weighted *w) { delete w; }
 
+int ib_w_create_csr(ib_weighted **out, int64_t nrow, int64_t ncol, const int32_t *rowptr, const int32_t *col, const double *val,
+                    const double *wM, const double *Mw, int conservative)
+{
+    IB_TRY
+    if (!out || nrow < 0 || ncol < 0 || !rowptr) fail(IB_ERR_ARG, "ib_w_create_csr: bad argument");
+    ensure_device();
+    const int64_t nnz = rowptr[nrow];
+    if (rowptr[0] != 0 || nnz < 0 || (nnz && (!col || !val))) fail(IB_ERR_ARG, "ib_w_create_csr: bad rowptr");
+    for (int64_t r = 0; r < nrow; ++r) if (rowptr[r + 1] < rowptr[r]) fail(IB_ERR_ARG, "ib_w_create_csr: rowptr not monotone");
+    for (int64_t j = 0; j < nnz; ++j) if (col[j] < 0 || col[j] >= ncol) fail(IB_ERR_ARG, "ib_w_create_csr: column index out of range");
+    cudaStream_t s = default_stream();
+    std::unique_ptr<ib_weighted> W(new ib_weighted);
+    W->w.reset(new Weighted);
+    Weighted &w = *W->w;
+    w.stream = s; w.nrow = nrow; w.ncol = ncol; w.nnz = nnz; w.conservative = conservative != 0;
+    for (int k = 0; k < 2; ++k) {
+        w.owned[k].reset(new Dim);
+        w.owned[k]->identity = true;
+        w.owned[k]->sparse_extent = w.owned[k]->dense_extent = k ? ncol : nrow;
+        w.dims[k] = w.owned[k].get();
+    }
+    w.rowptr.alloc((size_t)nrow + 1, s); w.rowptr.upload(rowptr, (size_t)nrow + 1);
+    w.col.alloc((size_t)nnz, s); w.col.upload(col, (size_t)nnz);
+    w.val.alloc((size_t)nnz, s); w.val.upload(val, (size_t)nnz);
+    w.wM.alloc((size_t)nrow, s); w.Mw.alloc((size_t)ncol, s);
+    if (wM) w.wM.upload(wM, (size_t)nrow); else w.wM.zero();
+    if (Mw) w.Mw.upload(Mw, (size_t)ncol); else w.Mw.zero();
+    IB_CUDA(cudaStreamSynchronize(s));
+    *out = W.release();
+    return IB_OK;
+    IB_CATCH
+}
+
 int ib_w_info(const ib_weighted *W, int64_t *info)
 {
     Weighted const &w = *W->w;

@@ -71,14 +71,15 @@ struct RegridMatrices {
     cudaStream_t stream = nullptr;
 };
 
-// SpMM work decomposition (apply.cu): rows are cut into chunks of <= CHUNK nonzeros
+// SpMM work decomposition (apply.cu): groups of short rows + chunks of long rows.  One apply at a time per matrix.
 struct ApplyPlan {
     bool ready = false;
     int64_t nitems = 0;
-    DBuf<int4> items;        // (row, begin, end, partial_slot or -1)
+    DBuf<int4> items;        // (first_row, nnz_begin, nnz_end, partial slot >= 0 | -(rows in group))
     int64_t nsplit_rows = 0;
-    DBuf<int4> split_rows;   // (row, first_partial, npartials, 0)
+    DBuf<int4> split_rows;   // (row, first_partial, nchunks, 0)
     int64_t npartials = 0;
+    DBuf<int32_t> slot_srow; // partial slot -> split-row index
 };
 
 // linear::Weighted_Eigen: CSR matrix (rows = output space) + weights + dims.

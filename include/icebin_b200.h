@@ -103,6 +103,11 @@ int ib_rm_matrix_d(ib_rm *, const char *spec, ib_dim *dim0, ib_dim *dim1, int sc
                    const double *sigma, ib_weighted **out);
 void ib_w_free(ib_weighted *);
 
+/* Extension (no upstream counterpart): wrap an existing dense-indexed CSR matrix + weights (e.g. one read back from
+ * a file written by Weighted_Eigen::ncio, matrix_formats.rst:9-63) so it can be applied on the GPU.  Identity dims. */
+int ib_w_create_csr(ib_weighted **out, int64_t nrow, int64_t ncol, const int32_t *rowptr, const int32_t *col,
+                    const double *val, const double *wM, const double *Mw, int conservative);
+
 /* info[0..7] = nrow, ncol, nnz, conservative, scaled, sparse_extent(dim0), sparse_extent(dim1), reserved */
 int ib_w_info(const ib_weighted *, int64_t *info);
 /* matrix in CSR (rows = output space, columns ascending inside a row) and as sorted COO (to_coo()) */
