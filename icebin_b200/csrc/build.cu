@@ -17,6 +17,7 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "types.cuh"
+#include "util.cuh"
 
 namespace ib {
 
@@ -293,18 +294,6 @@ struct ReduceApply {
     }
 };
 
-// ptr[r] = first j with idx[j] >= r  (idx ascending); ptr[nseg] = n
-__global__ void seg_ptr_kernel(const int32_t *idx, int64_t n, int64_t nseg, int32_t *ptr)
-{
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    int32_t r = idx[j];
-    int32_t prev = j > 0 ? idx[j - 1] : -1;
-    for (int32_t q = prev + 1; q <= r; ++q) ptr[q] = (int32_t)j;
-    if (j == n - 1)
-        for (int64_t q = (int64_t)r + 1; q <= nseg; ++q) ptr[q] = (int32_t)n;
-}
-
 // sequential (reference-order) sums: rows in CSR order, columns through the CSC permutation
 __global__ void row_sum_kernel(const int32_t *rowptr, const double *val, int64_t nrow, double *out)
 {
@@ -321,11 +310,6 @@ __global__ void col_sum_kernel(const int32_t *colptr, const uint32_t *perm, cons
     double s = 0;
     for (int32_t j = colptr[c]; j < colptr[c + 1]; ++j) s += val[perm[j]];
     out[c] = s;
-}
-__global__ void iota_u32_kernel(uint32_t *p, int64_t n)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = (uint32_t)i;
 }
 __global__ void gather_i32_kernel(const uint32_t *perm, const int32_t *src, int64_t n, int32_t *dst)
 {
@@ -374,13 +358,6 @@ __global__ void scale_vals_kernel(const int32_t *row, const int32_t *col, const 
     if (scale) v = f[row[j]] * v;
     if (use_cratio) v = v * cratio[col[j]];
     val[j] = v;
-}
-
-static int bits_for(int64_t n)
-{
-    int b = 1;
-    while ((int64_t(1) << b) < n) ++b;
-    return b;
 }
 
 struct SpecPlan {

@@ -192,7 +192,14 @@ int ib_gcm_add_sheet(ib_gcm *G, const char *name, int64_t nI, int32_t n_real_I, 
     for (int64_t i = 0; i < n_real_I && sh->dimI_identity; ++i) sh->dimI_identity = (dimI[i] == i);
     sh->dimI.alloc((size_t)n_real_I, s); sh->dimI.upload(dimI, (size_t)n_real_I);
     sh->native_areaI.alloc((size_t)n_real_I, s); sh->native_areaI.upload(native_areaI, (size_t)n_real_I);
-    if (centroid_xy) { sh->centroid_xy.alloc(2 * (size_t)n_real_I, s); sh->centroid_xy.upload(centroid_xy, 2 * (size_t)n_real_I); }
+    if (centroid_xy && n_real_I > 0) {
+        sh->centroid_xy.alloc(2 * (size_t)n_real_I, s); sh->centroid_xy.upload(centroid_xy, 2 * (size_t)n_real_I);
+        sh->bbox[0] = sh->bbox[1] = centroid_xy[0]; sh->bbox[2] = sh->bbox[3] = centroid_xy[1];
+        for (int64_t i = 0; i < n_real_I; ++i) {
+            sh->bbox[0] = std::min(sh->bbox[0], centroid_xy[2 * i]); sh->bbox[1] = std::max(sh->bbox[1], centroid_xy[2 * i]);
+            sh->bbox[2] = std::min(sh->bbox[2], centroid_xy[2 * i + 1]); sh->bbox[3] = std::max(sh->bbox[3], centroid_xy[2 * i + 1]);
+        }
+    }
     sh->ex_ij.alloc((size_t)nX, s); sh->ex_ij.upload(reinterpret_cast<const int2 *>(ex_ij), (size_t)nX);
     sh->ex_area.alloc((size_t)nX, s); sh->ex_area.upload(ex_area, (size_t)nX);
     // sApvA / sEpvE diagonal (IceRegridder.cpp:41-65): native/proj per realised A cell, 0 elsewhere ("missing")

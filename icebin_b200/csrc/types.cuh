@@ -37,6 +37,7 @@ struct Sheet {
     DBuf<double> native_areaI;     // [n_real_I]
     DBuf<double> centroid_xy;      // [n_real_I][2] (may be empty)
     bool dimI_identity = false;
+    double bbox[4] = {0, 0, 0, 0};   // x0, x1, y0, y1 of the centroids (smoothing bins)
     // aexgrid (AbbrGrid.hpp:40-78)
     DBuf<int2> ex_ij;              // [nX] (iA, iI)
     DBuf<double> ex_area;          // [nX]

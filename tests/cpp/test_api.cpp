@@ -51,7 +51,7 @@ int main(int argc, char **argv)
     auto EvI = rm->matrix("EvI");
     auto IvE = rm->matrix("IvE");
     auto AvI = rm->matrix("AvI");
-    CHECK(AvI->shape()[1] == 40 && AvI->nnz() == 40);          // 40 unmasked ice cells
+    CHECK(AvI->shape()[1] == 42 && AvI->nnz() == 42);          // 48 - 6 masked ice cells
     CHECK(EvI->conservative() && EvI->scaled());
     CHECK(EvI->dim(1) == IvE->dim(0) && EvI->dim(0) == IvE->dim(1));
 

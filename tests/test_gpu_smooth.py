@@ -1,0 +1,62 @@
+"""GPU parity of the sigma smoothing operator (K4) and of the conservation correction against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import make_gpu, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def csc_order(row, col, val):
+    o = np.lexsort((row, col))
+    return row[o], col[o], val[o]
+
+
+@pytest.mark.parametrize("spec", ["IvE", "IvA"])
+@pytest.mark.parametrize("sigma", [(100e3, 100e3, 300.0), (75e3, 120e3, np.inf), (60e3, 60e3, 150.0)])
+def test_smoothed_matrix_cfg1(cfg1, spec, sigma):
+    go, gg = make_oracle(cfg1), make_gpu(cfg1)
+    em = cfg1["elevmask"][0]
+    Wo = go.matrix(0, em, spec, scale=True, correctA=True, sigma=sigma)
+    Wg = gg.regrid_matrices(cfg1["sheets"][0].name, em, scale=True, correctA=True, sigma=sigma).matrix(spec)
+    assert not Wg.conservative and Wg.shape == Wo.shape and Wg.nnz == Wo.nnz
+    r, c, v = csc_order(*Wg.to_coo_dense())
+    assert np.array_equal(r, Wo.row) and np.array_equal(c, Wo.col)
+    np.testing.assert_allclose(v, Wo.val, rtol=1e-12, atol=0)
+    np.testing.assert_array_equal(Wg.get_weights(0), Wo.wM)
+    np.testing.assert_array_equal(Wg.get_weights(1), Wo.Mw)
+    # apply with and without the conservation correction
+    X = np.random.default_rng(0).uniform(0, 1, (5, Wo.shape[1]))
+    for fc in (False, True):
+        Yo, Yg = Wo.apply(X, force_conservation=fc), Wg.apply(X, force_conservation=fc)
+        np.testing.assert_allclose(Yg, Yo, rtol=1e-11, atol=0)
+    Yg = Wg.apply(X, force_conservation=True)
+    np.testing.assert_allclose((Yg * Wo.wM).sum(1), (X * Wo.Mw).sum(1), rtol=1e-12)
+
+
+def test_smoothed_cfg2(cfg2):
+    """The configs[2] operator: Greenland 5 km, sigma = (50 km, 50 km, 100 m)."""
+    go, gg = make_oracle(cfg2), make_gpu(cfg2)
+    em = cfg2["elevmask"][0]
+    sigma = (50e3, 50e3, 100.0)
+    Wo = go.matrix(0, em, "IvE", scale=True, correctA=True, sigma=sigma)
+    Wg = gg.regrid_matrices(cfg2["sheets"][0].name, em, scale=True, correctA=True, sigma=sigma).matrix("IvE")
+    r, c, v = csc_order(*Wg.to_coo_dense())
+    assert np.array_equal(r, Wo.row) and np.array_equal(c, Wo.col)
+    np.testing.assert_allclose(v, Wo.val, rtol=1e-12, atol=0)
+    X = np.random.default_rng(1).uniform(0, 1, (4, Wo.shape[1]))
+    np.testing.assert_allclose(Wg.apply(X), Wo.apply(X), rtol=1e-11)
+
+
+def test_smoothing_with_identity_dimI(cfg1):
+    """IceCoupler.cpp:461-463: IvE with sigma on an identity dimI holding all nI cells (masked cells -> empty rows)."""
+    from icebin_b200 import api
+    go, gg = make_oracle(cfg1), make_gpu(cfg1)
+    sh, em = cfg1["sheets"][0], cfg1["elevmask"][0]
+    sigma = (100e3, 100e3, 300.0)
+    dI, dE = api.SparseSet(identity=sh.nI), api.SparseSet()
+    Wg = gg.regrid_matrices(sh.name, em).matrix_d("IvE", (dI, dE), scale=True, correctA=True, sigma=sigma)
+    Wo = go.matrix(0, em, "IvE", scale=True, correctA=True, sigma=sigma, dims=(np.arange(sh.nI), np.zeros(0, np.int64)))
+    r, c, v = csc_order(*Wg.to_coo_dense())
+    assert np.array_equal(r, Wo.row) and np.array_equal(c, Wo.col)
+    np.testing.assert_allclose(v, Wo.val, rtol=1e-12, atol=0)
