@@ -57,6 +57,8 @@ SIGNATURES = {
     "ib_w_apply_weight": (C.c_int, [vp, C.c_int, vp, i32, vp]),
     "ib_coo_matvec": (C.c_int, [vp, vp, C.c_int, i64, i64, i64, vp, vp, vp]),
     "ib_multivec_to_dense": (C.c_int, [i64, vp, vp, vp, i32, i64, f64, vp, vp]),
+    "ib_merge_pack_dev": (C.c_int, [vp, i64, i32, vp, i64, vp, vp]),
+    "ib_merge_unpack_dev": (C.c_int, [vp, i64, i32, i64, vp, vp, vp, vp, vp]),
     "ib_hntr_create": (C.c_int, [PP, C.c_int, C.c_int, f64, f64, C.c_int, C.c_int, f64, f64, f64]),
     "ib_hntr_free": (None, [vp]),
     "ib_hntr_get": (C.c_int, [vp, C.c_int, vp, vp]),

@@ -59,6 +59,10 @@ void hntr_dims(Hntr const &, int *);
 void hntr_regrid_dev(Hntr &, const double *, double, double, const void *, int, double *, bool, cudaStream_t);
 int64_t hntr_matrix(Hntr &, double, int64_t *, int64_t *, double *, cudaStream_t);
 
+// merge.cu
+void merge_pack(const double *, int64_t, int, const int32_t *, int64_t, double *, cudaStream_t);
+void merge_unpack(double *, int64_t, int, int64_t, const int32_t *, const double *, const double *, const double *, cudaStream_t);
+
 // cell-major <-> field-major transposition: out[c*ldo + r] = in[r*ldi + c]
 __global__ void transpose_kernel(const double *__restrict__ in, int64_t ldi, int64_t nr, int64_t nc, double *__restrict__ out, int64_t ldo)
 {
@@ -567,6 +571,24 @@ int ib_multivec_to_dense(int64_t n, const int64_t *index, const double *weights,
         }
         for (int64_t i = 0; i < nE; ++i) if (std::isnan(d[i])) d[i] = fill;
     }
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_merge_pack_dev(const double *dY, int64_t ldy, int32_t nvar, const int32_t *d_loc, int64_t nshared, double *d_buf, void *stream)
+{
+    IB_TRY
+    ensure_device();
+    merge_pack(dY, ldy, nvar, d_loc, nshared, d_buf, stream ? (cudaStream_t)stream : default_stream());
+    return IB_OK;
+    IB_CATCH
+}
+int ib_merge_unpack_dev(double *dY, int64_t ldy, int32_t nvar, int64_t nrow, const int32_t *d_slot_of_row, const double *d_buf,
+                        const double *d_wtot, const double *d_wlocal, void *stream)
+{
+    IB_TRY
+    ensure_device();
+    merge_unpack(dY, ldy, nvar, nrow, d_slot_of_row, d_buf, d_wtot, d_wlocal, stream ? (cudaStream_t)stream : default_stream());
     return IB_OK;
     IB_CATCH
 }

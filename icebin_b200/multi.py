@@ -1,0 +1,98 @@
+"""Multi-GPU plumbing: one ice sheet per rank, A/E-grid contributions merged across sheets.
+
+Reference semantics: every sheet contributes sparse (index, weight = wM, vals = M_unscaled x) entries on the A (or E)
+grid (IceCoupler.cpp:445-457); the GCM side sums them and divides by the summed weights
+(VectorMultivec::to_dense_scale / to_dense, multivec.cpp:35-81).  Sheets are independent until this merge
+(GCMCoupler.cpp:491-497), so ranks exchange only the rows of cells that more than one sheet touches.
+
+torch.distributed is used for the collectives only (NCCL over NVLink on GPUs, gloo in the CPU tests); pack / unpack
+run in the library's own CUDA kernels (csrc/merge.cu).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def plan_shared(local_ids, n_sparse, group=None):
+    """All ranks pass the sparse ids of their dense rows (dims[0] of AvI / EvI).  Returns
+    (shared_ids, loc, slot_of_row): shared_ids = ascending sparse ids present on >= 2 ranks (identical on all ranks),
+    loc[k] = local dense row of shared_ids[k] or -1, slot_of_row[r] = k if local row r is shared else -1.
+    Works on any backend (CPU tensors with gloo, CUDA tensors with nccl)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    local_ids = np.asarray(local_ids, dtype=np.int64)
+    dev = torch.device("cuda", torch.cuda.current_device()) if (dist.is_initialized() and dist.get_backend(group) == "nccl") else torch.device("cpu")
+    cnt = torch.zeros(n_sparse, dtype=torch.int32, device=dev)
+    cnt[torch.from_numpy(local_ids).to(dev)] = 1
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    shared_ids = torch.nonzero(cnt >= 2).flatten().cpu().numpy().astype(np.int64)
+    pos = {int(s): r for r, s in enumerate(local_ids)}
+    loc = np.array([pos.get(int(s), -1) for s in shared_ids], dtype=np.int32)
+    slot_of_row = np.full(len(local_ids), -1, dtype=np.int32)
+    for k, r in enumerate(loc):
+        if r >= 0:
+            slot_of_row[r] = k
+    return shared_ids, loc, slot_of_row
+
+
+def merge_reference(contribs, n_sparse, fill=np.nan):
+    """Numpy statement of the merge for tests: contribs = [(ids, wM, num[nrow, nvar]), ...] -> dense [n_sparse, nvar]."""
+    nvar = contribs[0][2].shape[1]
+    num = np.zeros((n_sparse, nvar))
+    w = np.zeros(n_sparse)
+    touched = np.zeros(n_sparse, bool)
+    for ids, wM, vals in contribs:
+        np.add.at(num, ids, vals)
+        np.add.at(w, ids, wM)
+        touched[ids] = True
+    out = np.full((n_sparse, nvar), fill)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out[touched] = num[touched] * (1.0 / w[touched])[:, None]
+    return out
+
+
+class SheetMerge:
+    """Per-rank merge state for a set of (unscaled) matrices whose rows live on the A or E grid.  All matrices share
+    ONE packed buffer, so a step costs a single all-reduce."""
+
+    def __init__(self, spaces, nvar, device, group=None):
+        """spaces: list of (n_sparse, Weighted)."""
+        from ._lib import check, lib
+        self._lib, self._check = lib(), check
+        self.nvar, self.group = nvar, group
+        self.parts = []
+        off = 0
+        multi_rank = dist.is_initialized() and dist.get_world_size(group) > 1
+        for n_sparse, W in spaces:
+            shared_ids, loc, slot = plan_shared(W.dim(0), n_sparse, group)
+            part = dict(nrow=W.shape[0], nshared=len(shared_ids), off=off, shared_ids=shared_ids,
+                        loc=torch.from_numpy(loc).to(device), slot=torch.from_numpy(slot).to(device),
+                        wlocal=torch.from_numpy(W.get_weights(0)).to(device))
+            off += len(shared_ids)
+            self.parts.append(part)
+        self.nshared = off
+        self.buf = torch.zeros((max(off, 1), nvar), dtype=torch.float64, device=device)
+        # summed weights of the shared cells (they change only when the matrices are rebuilt)
+        self.wtot = torch.zeros(max(off, 1), dtype=torch.float64, device=device)
+        for p in self.parts:
+            have = p["loc"] >= 0
+            if p["nshared"]:
+                seg = self.wtot[p["off"]: p["off"] + p["nshared"]]
+                seg[have] = p["wlocal"][p["loc"][have].long()]
+        if off and multi_rank:
+            dist.all_reduce(self.wtot, group=group)
+        self._multi = multi_rank
+
+    def run(self, Ys, stream):
+        """Ys[i] [nrow_i, nvar] holds this sheet's unscaled sums; on return they hold the merged, scaled values."""
+        L, nvar = self._lib, self.nvar
+        for p, Y in zip(self.parts, Ys):
+            if p["nshared"]:
+                self._check(L.ib_merge_pack_dev(Y.data_ptr(), nvar, nvar, p["loc"].data_ptr(), p["nshared"],
+                                                self.buf.data_ptr() + p["off"] * nvar * 8, stream))
+        if self.nshared and self._multi:
+            dist.all_reduce(self.buf, group=self.group)             # NCCL sum over NVLink on the current stream
+        for p, Y in zip(self.parts, Ys):
+            self._check(L.ib_merge_unpack_dev(Y.data_ptr(), nvar, nvar, p["nrow"], p["slot"].data_ptr(),
+                                              self.buf.data_ptr() + p["off"] * nvar * 8, self.wtot.data_ptr() + p["off"] * 8,
+                                              p["wlocal"].data_ptr(), stream))

@@ -142,6 +142,14 @@ int ib_coo_matvec(double *yy, const double *xx, int ignore_nan, int64_t nrow, in
 int ib_multivec_to_dense(int64_t n, const int64_t *index, const double *weights, const double *vals, int32_t nvar,
                          int64_t nE, double fill, double *scaleE, double *dense);
 
+/* Device-resident form of the same merge, one ice sheet per GPU (see icebin_b200/multi.py): pack the rows of the
+ * cells shared with other sheets (loc[k] = local dense row of shared cell k, or -1), all-reduce `buf` across ranks
+ * (NCCL, by the caller), then unpack: shared rows <- buf / wtot, other rows <- Y / wlocal. */
+int ib_merge_pack_dev(const double *dY, int64_t ldy, int32_t nvar, const int32_t *d_loc, int64_t nshared, double *d_buf,
+                      void *stream);
+int ib_merge_unpack_dev(double *dY, int64_t ldy, int32_t nvar, int64_t nrow, const int32_t *d_slot_of_row,
+                        const double *d_buf, const double *d_wtot, const double *d_wlocal, void *stream);
+
 /* ---- Hntr ------------------------------------------------------------------------------------------ */
 /* Hntr(yp17, Bspec, Aspec, DATMIS); HntrSpec(im, jm, offi, dlat[minutes])   hntr.cpp:63-82, GridSpec.hpp:143-170 */
 int ib_hntr_create(ib_hntr **out, int imB, int jmB, double offiB, double dlatB, int imA, int jmA, double offiA,
