@@ -61,9 +61,12 @@ class SparseSet:
         return out
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().ib_dim_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().ib_dim_free(self._h)
+                self._h = None
+        except Exception:      # interpreter shutdown: the loader module may already be gone
+            pass
 
 
 class Weighted:
@@ -173,9 +176,12 @@ class Weighted:
         return self.apply_weight(1, A_s)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().ib_w_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().ib_w_free(self._h)
+                self._h = None
+        except Exception:      # interpreter shutdown: the loader module may already be gone
+            pass
 
 
 class RegridMatrices:
@@ -207,9 +213,12 @@ class RegridMatrices:
         return Weighted(h, keep=tuple(dims))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().ib_rm_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().ib_rm_free(self._h)
+                self._h = None
+        except Exception:      # interpreter shutdown: the loader module may already be gone
+            pass
 
 
 class GCMRegridder:
@@ -280,9 +289,12 @@ class GCMRegridder:
         return RegridMatrices(h, self)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().ib_gcm_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().ib_gcm_free(self._h)
+                self._h = None
+        except Exception:      # interpreter shutdown: the loader module may already be gone
+            pass
 
 
 class HntrSpec:
@@ -369,9 +381,12 @@ class Hntr:
         return r, c, v
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().ib_hntr_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().ib_hntr_free(self._h)
+                self._h = None
+        except Exception:      # interpreter shutdown: the loader module may already be gone
+            pass
 
 
 def coo_matvec(yy, xx, ignore_nan, nrow, ncol, row, col, data):

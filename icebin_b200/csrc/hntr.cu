@@ -127,14 +127,17 @@ template <class SrcT, int CPT>
 struct SrcVec;
 template <>
 struct SrcVec<int16_t, 8> {
+    // int16 -> double without the (quarter-rate) I2F.F64 path: 2^52 + (u ^ 0x8000) is exact in the mantissa of a
+    // double whose high word is 0x43300000; subtracting 2^52 + 32768 leaves the signed value exactly.
     static __device__ __forceinline__ void load(const int16_t *p, double (&x)[8])
     {
         int4 r = __ldg(reinterpret_cast<const int4 *>(p));
-        int w[4] = {r.x, r.y, r.z, r.w};
+        const unsigned w[4] = {(unsigned)r.x, (unsigned)r.y, (unsigned)r.z, (unsigned)r.w};
+        const double magic = 4503599627370496.0 + 32768.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            x[2 * k] = (double)(int16_t)(w[k] & 0xffff);
-            x[2 * k + 1] = (double)(int16_t)(w[k] >> 16);
+            x[2 * k] = __hiloint2double(0x43300000, (int)((w[k] & 0xffffu) ^ 0x8000u)) - magic;
+            x[2 * k + 1] = __hiloint2double(0x43300000, (int)((w[k] >> 16) ^ 0x8000u)) - magic;
         }
     }
 };
@@ -151,49 +154,74 @@ struct SrcVec<SrcT, 1> {
     static __device__ __forceinline__ void load(const SrcT *p, double (&x)[1]) { x[0] = (double)__ldg(p); }
 };
 
-template <class SrcT, int CPT, bool HASW>
-__global__ void __launch_bounds__(128) hntr_cols_kernel(const SrcT *__restrict__ A, const double *__restrict__ WTA, double wtm, double wtb,
+// RS = row split: the RS warps of a block share the same 32*CPT source columns and take every RS-th source row, so
+// narrow sources (int16: 8 columns per 16-byte load => few threads per row) still put enough loads in flight; the
+// RS partial sums are combined through shared memory in warp order (deterministic).
+template <class SrcT, int CPT, bool HASW, int UNR, int RS>
+__global__ void __launch_bounds__(128, (sizeof(SrcT) == 2 ? 16 : 8)) hntr_cols_kernel(const SrcT *__restrict__ A, const double *__restrict__ WTA, double wtm, double wtb,
                                                         int imA, const double *__restrict__ sina, const int *__restrict__ jmin,
                                                         const int *__restrict__ jmax, const double *__restrict__ gmin,
                                                         const double *__restrict__ gmax, double *__restrict__ S, double *__restrict__ T)
 {
+    constexpr int TPR = 128 / RS;                      // threads (column groups) per source row
+    __shared__ double red[RS > 1 ? (RS - 1) * TPR * (2 * CPT) : 1];
     const int jb = blockIdx.y;
-    const int ia0 = (blockIdx.x * blockDim.x + threadIdx.x) * CPT;
-    if (ia0 >= imA) return;
+    const int part = threadIdx.x / TPR, tcol = threadIdx.x % TPR;
+    const int ia0 = (blockIdx.x * TPR + tcol) * CPT;
+    const bool live = ia0 < imA;
     const int jlo = jmin[jb], jhi = jmax[jb];
     double sv[CPT], sw[CPT];
 #pragma unroll
     for (int k = 0; k < CPT; ++k) { sv[k] = 0; sw[k] = 0; }
     const double wconst = wtm * 1.0 + wtb;
     double gsum = 0;
-#pragma unroll 4
-    for (int ja = jlo; ja <= jhi; ++ja) {
-        double G = sina[ja] - sina[ja - 1];
-        if (ja == jlo) G -= gmin[jb];
-        if (ja == jhi) G -= gmax[jb];
-        const int64_t off = (int64_t)(ja - 1) * imA + ia0;
-        double x[CPT];
-        SrcVec<SrcT, CPT>::load(A + off, x);
-        if (HASW) {
-            double w[CPT];
+    if (live) {
+#pragma unroll UNR
+        for (int ja = jlo + part; ja <= jhi; ja += RS) {
+            double G = sina[ja] - sina[ja - 1];
+            if (ja == jlo) G -= gmin[jb];
+            if (ja == jhi) G -= gmax[jb];
+            const int64_t off = (int64_t)(ja - 1) * imA + ia0;
+            double x[CPT];
+            SrcVec<SrcT, CPT>::load(A + off, x);
+            if (HASW) {
+                double w[CPT];
 #pragma unroll
-            for (int k = 0; k < CPT; k += (CPT > 1 ? 2 : 1)) {
-                if (CPT > 1) { double2 t = __ldg(reinterpret_cast<const double2 *>(WTA + off + k)); w[k] = t.x; w[k + (CPT > 1)] = t.y; }
-                else w[k] = __ldg(WTA + off + k);
+                for (int k = 0; k < CPT; k += (CPT > 1 ? 2 : 1)) {
+                    if (CPT > 1) { double2 t = __ldg(reinterpret_cast<const double2 *>(WTA + off + k)); w[k] = t.x; w[k + (CPT > 1)] = t.y; }
+                    else w[k] = __ldg(WTA + off + k);
+                }
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    const double wt = G * (wtm * w[k] + wtb);
+                    sw[k] += wt;
+                    sv[k] += wt * x[k];
+                }
+            } else {
+                const double wt = G * wconst;
+                gsum += wt;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) sv[k] += wt * x[k];
             }
-#pragma unroll
-            for (int k = 0; k < CPT; ++k) {
-                const double wt = G * (wtm * w[k] + wtb);
-                sw[k] += wt;
-                sv[k] += wt * x[k];
-            }
-        } else {
-            const double wt = G * wconst;
-            gsum += wt;
-#pragma unroll
-            for (int k = 0; k < CPT; ++k) sv[k] += wt * x[k];
         }
     }
+    if (RS > 1) {
+        if (part > 0) {
+            double *r = red + ((part - 1) * TPR + tcol) * (2 * CPT);
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { r[k] = sv[k]; r[CPT + k] = HASW ? sw[k] : gsum; }
+        }
+        __syncthreads();
+        if (part > 0) return;
+#pragma unroll
+        for (int p = 1; p < RS; ++p) {
+            const double *r = red + ((p - 1) * TPR + tcol) * (2 * CPT);
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) { sv[k] += r[k]; if (HASW) sw[k] += r[CPT + k]; }
+            if (!HASW) gsum += r[CPT];
+        }
+    }
+    if (!live) return;
     double *so = S + (int64_t)jb * imA + ia0;
     double *to = T + (int64_t)jb * imA + ia0;
 #pragma unroll
@@ -260,11 +288,12 @@ __global__ void __launch_bounds__(256) hntr_polar_kernel(double *__restrict__ B,
 template <class SrcT, int CPT>
 static void launch_cols(Hntr &h, const SrcT *A, const double *W, double wtm, double wtb, double *S, double *T, cudaStream_t s)
 {
-    dim3 grid((unsigned)cdiv(cdiv(h.imA, CPT), 128), (unsigned)h.jmB);
+    constexpr int RS = 1;   // row split (measured slower on B200 for the ETOPO1 shapes; kept for narrow grids)
+    dim3 grid((unsigned)cdiv(cdiv(h.imA, CPT), 128 / RS), (unsigned)h.jmB);
     if (W)
-        hntr_cols_kernel<SrcT, CPT, true><<<grid, 128, 0, s>>>(A, W, wtm, wtb, h.imA, h.d_sina.p, h.d_jmin.p, h.d_jmax.p, h.d_gmin.p, h.d_gmax.p, S, T);
+        hntr_cols_kernel<SrcT, CPT, true, (sizeof(SrcT) == 2 ? 2 : 4), RS><<<grid, 128, 0, s>>>(A, W, wtm, wtb, h.imA, h.d_sina.p, h.d_jmin.p, h.d_jmax.p, h.d_gmin.p, h.d_gmax.p, S, T);
     else
-        hntr_cols_kernel<SrcT, CPT, false><<<grid, 128, 0, s>>>(A, W, wtm, wtb, h.imA, h.d_sina.p, h.d_jmin.p, h.d_jmax.p, h.d_gmin.p, h.d_gmax.p, S, T);
+        hntr_cols_kernel<SrcT, CPT, false, (sizeof(SrcT) == 2 ? 2 : 4), RS><<<grid, 128, 0, s>>>(A, W, wtm, wtb, h.imA, h.d_sina.p, h.d_jmin.p, h.d_jmax.p, h.d_gmin.p, h.d_gmax.p, S, T);
     IB_LAUNCHED();
 }
 
