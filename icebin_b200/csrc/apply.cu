@@ -23,8 +23,10 @@
 // Roofline: HBM.  Algorithmic bytes = 12*nnz + 4*(nrow+1) + 8*nvar*(ncol_touched + nrow)   (SURVEY 8d).
 #include <cstdlib>
 
+#include "radix_sort.cuh"
 #include "scan.cuh"
 #include "types.cuh"
+#include "util.cuh"
 
 namespace ib {
 
@@ -76,6 +78,8 @@ struct PlanApply {
     }
 };
 
+static bool make_pair_plan(Weighted &W, cudaStream_t s);
+
 static void make_plan(Weighted &W, cudaStream_t s)
 {
     ApplyPlan &P = W.plan;
@@ -93,8 +97,216 @@ static void make_plan(Weighted &W, cudaStream_t s)
         P.split_rows.alloc((size_t)P.nsplit_rows, s);
         P.slot_srow.alloc((size_t)P.npartials, s);
         scan_apply<uint4>(st, L, AddU32x4{}, z, PlanApply{L, W.nrow, P.items.p, P.split_rows.p, P.slot_srow.p}, s);
+        make_pair_plan(W, s);
     }
     P.ready = true;
+}
+
+// ---- pair-grouped column plan ------------------------------------------------------------------------------
+// EvI-like matrices have (at most) two nonzeros per COLUMN: an ice cell feeds the two elevation classes that bracket
+// its elevation (IceRegridder_L0.cpp:126-143).  Row-wise processing then reads every X row twice.  Instead, columns
+// are regrouped by the pair of rows (r0, r1) they feed; a chunk of <= APPLY_CHUNK such columns is one item that reads
+// each X row ONCE and accumulates two partial rows (weights v0 -> r0, v1 -> r1).  Every output row is then the sum,
+// in a fixed order, of the partial rows listed for it (fx_ptr/fx_slot).
+__global__ void expand_rows_kernel(const int32_t *rowptr, int64_t nrow, int32_t *row)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrow) return;
+    for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) row[j] = (int32_t)r;
+}
+__global__ void u32_to_i32_copy_kernel(const uint32_t *a, int64_t n, int32_t *b)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (int32_t)a[i];
+}
+// A column with n nonzeros becomes ceil(n/2) "virtual columns", each owning two consecutive nonzeros of the column
+// (ice cells on the border between GCM cells feed 4 or 8 elevation classes).  vcount -> scan -> vbase.
+struct VCountLoad {
+    const int32_t *colptr;
+    __device__ uint32_t operator()(int64_t c) const { return (uint32_t)((colptr[c + 1] - colptr[c] + 1) / 2); }
+};
+// per virtual column: key = (r0 << 32 | r1 + 1), owning column, first CSC entry
+struct VEmit {
+    const int32_t *colptr;
+    const uint32_t *perm;
+    const int32_t *row;
+    uint64_t *key;
+    uint32_t *vid, *vcol, *vent;
+    __device__ void operator()(int64_t c, uint32_t base, uint32_t nv) const
+    {
+        const int b = colptr[c], e = colptr[c + 1];
+        for (uint32_t i = 0; i < nv; ++i) {
+            const int q = b + 2 * (int)i;
+            const uint32_t r0 = (uint32_t)row[perm[q]];
+            const uint32_t r1p = (q + 1 < e) ? (uint32_t)row[perm[q + 1]] + 1u : 0u;
+            key[base + i] = ((uint64_t)r0 << 32) | r1p;
+            vid[base + i] = base + i;
+            vcol[base + i] = (uint32_t)c;
+            vent[base + i] = (uint32_t)q;
+        }
+    }
+};
+// position p in the regrouped stream: x = starts an item, y = (position valid)
+struct PairLoad {
+    const uint64_t *key;
+    const uint32_t *gstart;      // group start of every position
+    __device__ uint32_t operator()(int64_t p) const { return ((uint32_t)p - gstart[p]) % APPLY_CHUNK == 0 ? 1u : 0u; }
+};
+struct GroupStartLoad {          // max-scan of (head ? p + 1 : 0)
+    const uint64_t *key;
+    __device__ uint32_t operator()(int64_t p) const { return (p == 0 || key[p] != key[p - 1]) ? (uint32_t)p + 1u : 0u; }
+};
+struct MaxU32 {
+    __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+struct GroupStartStore {
+    const uint64_t *key;
+    uint32_t *gstart;
+    __device__ void operator()(int64_t p, uint32_t prefix, uint32_t mine) const { gstart[p] = (mine ? mine : prefix) - 1u; }
+};
+struct PairEmit {
+    const uint64_t *key;
+    const uint32_t *vid, *vcol, *vent;   // vid: sorted order -> virtual column
+    const int32_t *colptr;
+    const uint32_t *perm;
+    const double *val;
+    int64_t nv;
+    int4 *items;
+    int32_t *pcol;
+    double *pv0, *pv1;
+    uint32_t *fxkey, *fxslot;    // [2*nitems] (row, slot) pairs for the fix-up lists; row = 0xffffffff if unused
+    __device__ void operator()(int64_t p, uint32_t prefix, uint32_t start) const
+    {
+        const uint64_t k = key[p];
+        const uint32_t v = vid[p];
+        const uint32_t c = vcol[v], q = vent[v];
+        pcol[p] = (int32_t)c;
+        pv0[p] = val[perm[q]];
+        pv1[p] = ((int)q + 1 < colptr[c + 1]) ? val[perm[q + 1]] : 0.0;
+        if (!start) return;
+        int64_t e = p + 1;
+        while (e < nv && e - p < APPLY_CHUNK && key[e] == k) ++e;
+        const int32_t r0 = (int32_t)(k >> 32), r1 = (int32_t)(uint32_t)k - 1;
+        items[prefix] = make_int4(r0, (int)p, (int)e, (int)(2 * prefix));
+        fxkey[2 * prefix] = (uint32_t)r0; fxslot[2 * prefix] = 2 * prefix;
+        fxkey[2 * prefix + 1] = r1 >= 0 ? (uint32_t)r1 : 0xffffffffu; fxslot[2 * prefix + 1] = 2 * prefix + 1;
+    }
+};
+
+static bool make_pair_plan(Weighted &W, cudaStream_t s)
+{
+    ApplyPlan &P = W.plan;
+    const int64_t nnz = W.nnz, ncol = W.ncol, nrow = W.nrow;
+    if (getenv("IB_SPMM_NOPAIR")) return false;
+    if (nnz < 1024 || 10 * nnz < 14 * ncol || nnz > 3 * ncol) return false;      // need ~2 nonzeros in most columns
+    // CSC view: stable sort of the nonzeros by column
+    DBuf<int32_t> row((size_t)nnz, s), csorted((size_t)nnz, s), colptr((size_t)ncol + 1, s);
+    DBuf<uint32_t> k0((size_t)nnz, s), k1((size_t)nnz, s), p0((size_t)nnz, s), p1((size_t)nnz, s);
+    expand_rows_kernel<<<(unsigned)cdiv(nrow, 128), 128, 0, s>>>(W.rowptr.p, nrow, row.p);
+    IB_LAUNCHED();
+    IB_CUDA(cudaMemcpyAsync(k0.p, W.col.p, nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    iota_u32_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(p0.p, nnz);
+    IB_LAUNCHED();
+    const int w1 = radix_sort_pairs<uint32_t, uint32_t>(k0.p, p0.p, k1.p, p1.p, nnz, bits_for(ncol), s);
+    const uint32_t *perm = w1 ? p1.p : p0.p;
+    u32_to_i32_copy_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(w1 ? k1.p : k0.p, nnz, csorted.p);
+    IB_LAUNCHED();
+    colptr.zero();
+    seg_ptr_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(csorted.p, nnz, ncol, colptr.p);
+    IB_LAUNCHED();
+    // virtual columns, regrouped by the pair of rows (r0, r1) they feed
+    ScanState<uint32_t> vs;
+    transform_scan<uint32_t>(vs, ncol, VCountLoad{colptr.p}, AddU32{}, 0u, s);
+    uint32_t nv_u = 0;
+    IB_CUDA(cudaMemcpyAsync(&nv_u, vs.total.p, sizeof nv_u, cudaMemcpyDeviceToHost, s));
+    IB_CUDA(cudaStreamSynchronize(s));
+    const int64_t nv = nv_u;
+    if (nv == 0 || 10 * nv > 7 * nnz) return false;            // not enough sharing to pay for the partial rows
+    DBuf<uint64_t> key0((size_t)nv, s), key1((size_t)nv, s);
+    DBuf<uint32_t> vid0((size_t)nv, s), vid1((size_t)nv, s), vcol((size_t)nv, s), vent((size_t)nv, s), gstart((size_t)nv, s);
+    scan_apply<uint32_t>(vs, VCountLoad{colptr.p}, AddU32{}, 0u, VEmit{colptr.p, perm, row.p, key0.p, vid0.p, vcol.p, vent.p}, s);
+    const int w2 = radix_sort_pairs<uint64_t, uint32_t>(key0.p, vid0.p, key1.p, vid1.p, nv, 32 + bits_for(nrow + 1), s);
+    const uint64_t *key = w2 ? key1.p : key0.p;
+    const uint32_t *vid = w2 ? vid1.p : vid0.p;
+    ScanState<uint32_t> gs, is;
+    transform_scan<uint32_t>(gs, nv, GroupStartLoad{key}, MaxU32{}, 0u, s);
+    scan_apply<uint32_t>(gs, GroupStartLoad{key}, MaxU32{}, 0u, GroupStartStore{key, gstart.p}, s);
+    transform_scan<uint32_t>(is, nv, PairLoad{key, gstart.p}, AddU32{}, 0u, s);
+    uint32_t nitems = 0;
+    IB_CUDA(cudaMemcpyAsync(&nitems, is.total.p, sizeof nitems, cudaMemcpyDeviceToHost, s));
+    IB_CUDA(cudaStreamSynchronize(s));
+    if (nitems == 0 || nv < 12 * (int64_t)nitems) return false;      // row pairs are not shared by enough columns
+    P.pair_nitems = nitems;
+    P.pair_items.alloc(nitems, s);
+    P.pcol.alloc((size_t)nv, s);
+    P.pv0.alloc((size_t)nv, s);
+    P.pv1.alloc((size_t)nv, s);
+    DBuf<uint32_t> fk0(2 * (size_t)nitems, s), fk1(2 * (size_t)nitems, s), fs0(2 * (size_t)nitems, s), fs1(2 * (size_t)nitems, s);
+    scan_apply<uint32_t>(is, PairLoad{key, gstart.p}, AddU32{}, 0u,
+                         PairEmit{key, vid, vcol.p, vent.p, colptr.p, perm, W.val.p, nv, P.pair_items.p, P.pcol.p, P.pv0.p, P.pv1.p, fk0.p, fs0.p}, s);
+    // fix-up lists: (row, slot) sorted by row, slots ascending inside a row (stable)
+    const int64_t nfx = 2 * (int64_t)nitems;
+    const int w3 = radix_sort_pairs<uint32_t, uint32_t>(fk0.p, fs0.p, fk1.p, fs1.p, nfx, 32, s);
+    DBuf<int32_t> fxrow((size_t)nfx, s);
+    u32_to_i32_copy_kernel<<<(unsigned)cdiv(nfx, 256), 256, 0, s>>>(w3 ? fk1.p : fk0.p, nfx, fxrow.p);   // 0xffffffff -> -1
+    IB_LAUNCHED();
+    // unused second slots carry row -1 after the cast and sort last (as 0xffffffff); count the valid prefix
+    P.fx_ptr.alloc((size_t)nrow + 1, s);
+    P.fx_ptr.zero();
+    P.fx_slot.alloc((size_t)nfx, s);
+    IB_CUDA(cudaMemcpyAsync(P.fx_slot.p, w3 ? fs1.p : fs0.p, nfx * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    std::vector<int32_t> hrow((size_t)nfx);
+    fxrow.download(hrow.data(), (size_t)nfx);
+    IB_CUDA(cudaStreamSynchronize(s));
+    int64_t nvalid = nfx;
+    while (nvalid > 0 && hrow[nvalid - 1] < 0) --nvalid;
+    if (nvalid > 0) {
+        seg_ptr_kernel<<<(unsigned)cdiv(nvalid, 256), 256, 0, s>>>(fxrow.p, nvalid, nrow, P.fx_ptr.p);
+        IB_LAUNCHED();
+    }
+    IB_CUDA(cudaStreamSynchronize(s));
+    P.pair = true;
+    return true;
+}
+
+// Y[r] = sum of the partial rows listed for r (fixed order); rows without partials are zero
+template <int VEC>
+__global__ void __launch_bounds__(256) spmm_fixup_list_kernel(const int32_t *__restrict__ fx_ptr, const uint32_t *__restrict__ fx_slot,
+                                                              int64_t nrow, const double *__restrict__ partials, int64_t ldp, int nvar,
+                                                              double *__restrict__ Y, int64_t ldy)
+{
+    const int nv = nvar / VEC;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r = t / nv;
+    int f = (int)(t - r * nv) * VEC;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched with programmatic stream serialization
+    if (r >= nrow) return;
+    const int b = fx_ptr[r], e = fx_ptr[r + 1];
+    double s[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) s[k] = 0.0;
+    int q = b;
+    for (; q + 4 <= e; q += 4) {
+        double p[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double *pp = partials + (int64_t)fx_slot[q + u] * ldp + f;
+            if (VEC == 2) { double2 tt = __ldcg(reinterpret_cast<const double2 *>(pp)); p[u][0] = tt.x; p[u][VEC - 1] = tt.y; }
+            else p[u][0] = __ldcg(pp);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) s[k] = s[k] + p[u][k];
+    }
+    for (; q < e; ++q) {
+        const double *pp = partials + (int64_t)fx_slot[q] * ldp + f;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s[k] = s[k] + __ldcg(pp + k);
+    }
+    double *out = Y + r * ldy + f;
+    if (VEC == 2) *reinterpret_cast<double2 *>(out) = make_double2(s[0], s[VEC - 1]);
+    else out[0] = s[0];
 }
 
 // ---- TMA (cp.async.bulk) pipeline -----------------------------------------------------------------------
@@ -134,7 +346,7 @@ struct SpmmArgs {
     int64_t nunits;
     int ntile, tw, nstage;
     const int32_t *rowptr, *col;
-    const double *val, *X;
+    const double *val, *val1, *X;     // val1 != nullptr: pair items (two output rows per column chunk)
     int64_t ldx;
     int nvar;
     double *Y;
@@ -143,6 +355,12 @@ struct SpmmArgs {
     int64_t ldp;
 };
 
+// Shared-memory stage = [TMA_ROWS rows of X][header: TMA_ROWS values (+ TMA_ROWS second values)]; the producer
+// also delivers the matrix values of the stage through the header, so consumers touch global memory only to read the
+// (prefetched) item record and to write results.
+constexpr uint32_t TMA_HDR = 2 * TMA_ROWS * 8;
+
+template <bool PAIR>
 __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const SpmmArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -150,7 +368,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
     uint64_t *empty = full + a.nstage;
     unsigned char *data = smem_raw + 256;           // 2*nstage*8 <= 248
     const uint32_t rowbytes = (uint32_t)a.tw * 8u;
-    const uint32_t stagebytes = rowbytes * TMA_ROWS;
+    const uint32_t stagebytes = rowbytes * TMA_ROWS + TMA_HDR;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, TMA_CONSUMERS / 32); }
@@ -159,34 +377,49 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
     __syncthreads();
     int stage = 0;
     uint32_t phase = 0;
+    int64_t u = blockIdx.x;
+    int4 it_next = u < a.nunits ? a.items[u / a.ntile] : make_int4(0, 0, 0, 0);
     if (warp == TMA_CONSUMERS / 32) {
-        // ===== producer warp: lanes 0..nr-1 each issue one row copy of the stage
-        for (int64_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+        // ===== producer warp: lanes 0..nr-1 each issue one row copy of the stage and post its matrix value(s)
+        for (; u < a.nunits; u += gridDim.x) {
             const int64_t item = u / a.ntile;
             const int tile = (int)(u - item * a.ntile);
-            const int4 it = a.items[item];
+            const int4 it = it_next;
+            if (u + gridDim.x < a.nunits) it_next = a.items[(u + gridDim.x) / a.ntile];
             const int f0 = tile * a.tw;
             const uint32_t tb = (uint32_t)min(a.tw, a.nvar - f0) * 8u;
             for (int j = it.y; j < it.z; j += TMA_ROWS) {
                 const int nr = min(TMA_ROWS, it.z - j);
-                const int c = (lane < nr) ? __ldg(a.col + j + lane) : 0;
-                if (lane == 0) {
-                    mbar_wait(empty + stage, phase ^ 1u);
-                    mbar_expect_tx(full + stage, tb * (uint32_t)nr);
+                int c = 0;
+                double v = 0.0, v1 = 0.0;
+                if (lane < nr) {
+                    c = __ldg(a.col + j + lane);
+                    v = __ldg(a.val + j + lane);
+                    if (PAIR) v1 = __ldg(a.val1 + j + lane);
+                }
+                if (lane == 0) mbar_wait(empty + stage, phase ^ 1u);
+                __syncwarp();
+                unsigned char *sp = data + (size_t)stage * stagebytes;
+                if (lane < TMA_ROWS) {
+                    double *hdr = reinterpret_cast<double *>(sp + (size_t)TMA_ROWS * rowbytes);
+                    hdr[lane] = v;
+                    if (PAIR) hdr[TMA_ROWS + lane] = v1;
                 }
                 __syncwarp();
-                if (lane < nr)
-                    bulk_g2s(data + (size_t)stage * stagebytes + (size_t)lane * rowbytes, a.X + (int64_t)c * a.ldx + f0, tb, full + stage);
+                if (lane == 0) mbar_expect_tx(full + stage, tb * (uint32_t)nr);      // arrive (release) after the header stores
+                __syncwarp();
+                if (lane < nr) bulk_g2s(sp + (size_t)lane * rowbytes, a.X + (int64_t)c * a.ldx + f0, tb, full + stage);
                 if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
         // ===== consumer warps: thread t owns fields f0 + 2t, f0 + 2t + 1
         const int t = threadIdx.x;
-        for (int64_t u = blockIdx.x; u < a.nunits; u += gridDim.x) {
+        for (; u < a.nunits; u += gridDim.x) {
             const int64_t item = u / a.ntile;
             const int tile = (int)(u - item * a.ntile);
-            const int4 it = a.items[item];
+            const int4 it = it_next;
+            if (u + gridDim.x < a.nunits) it_next = a.items[(u + gridDim.x) / a.ntile];
             const int f0 = tile * a.tw;
             const bool active = 2 * t < min(a.tw, a.nvar - f0);
             const int nrows = it.w < 0 ? -it.w : 0;
@@ -194,7 +427,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
             int my_end = (lane < nrows) ? __ldg(a.rowptr + it.x + lane + 1) : 0;
             int cur = 0;
             int cur_end = nrows ? __shfl_sync(0xffffffffu, my_end, 0) : it.z;
-            double a0 = 0.0, a1 = 0.0;
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
             int j = it.y;
             // leading empty rows of a group
             while (cur < nrows && cur_end == j) {
@@ -204,18 +437,23 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
             }
             for (int jb = it.y; jb < it.z; jb += TMA_ROWS) {
                 const int nr = min(TMA_ROWS, it.z - jb);
-                double v[TMA_ROWS];
-#pragma unroll
-                for (int r = 0; r < TMA_ROWS; ++r) v[r] = (r < nr) ? __ldg(a.val + jb + r) : 0.0;
                 mbar_wait(full + stage, phase);
-                const unsigned char *sp = data + (size_t)stage * stagebytes + (size_t)t * 16;
+                const unsigned char *sb = data + (size_t)stage * stagebytes;
+                const double *hdr = reinterpret_cast<const double *>(sb + (size_t)TMA_ROWS * rowbytes);
+                const unsigned char *sp = sb + (size_t)t * 16;
 #pragma unroll
                 for (int r = 0; r < TMA_ROWS; ++r) {
                     if (r < nr) {
                         if (active) {
                             const double2 x = *reinterpret_cast<const double2 *>(sp + (size_t)r * rowbytes);
-                            a0 = a0 + v[r] * x.x;
-                            a1 = a1 + v[r] * x.y;
+                            const double v = hdr[r];
+                            a0 = a0 + v * x.x;
+                            a1 = a1 + v * x.y;
+                            if (PAIR) {
+                                const double w = hdr[TMA_ROWS + r];
+                                b0 = b0 + w * x.x;
+                                b1 = b1 + w * x.y;
+                            }
                         }
                         ++j;
                         while (cur < nrows && cur_end == j) {      // row(s) of a group complete
@@ -230,8 +468,10 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
                 if (lane == 0) mbar_arrive(empty + stage);
                 if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
             }
-            if (it.w >= 0 && active)   // chunk of a long row: partial sum, combined in chunk order by spmm_fixup_kernel
+            if (it.w >= 0 && active) {  // chunk: partial sum(s), combined in a fixed order by the fix-up kernel
                 reinterpret_cast<double2 *>(a.partials + (int64_t)it.w * a.ldp + f0)[t] = make_double2(a0, a1);
+                if (PAIR) reinterpret_cast<double2 *>(a.partials + (int64_t)(it.w + 1) * a.ldp + f0)[t] = make_double2(b0, b1);
+            }
         }
     }
 }
@@ -305,6 +545,7 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const int4 *__restrict_
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t r = t / nv;
     int f = (int)(t - r * nv) * VEC;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched with programmatic stream serialization
     if (r >= nsplit) return;
     const int4 sr = split_rows[r];
     const double *pp = partials + (int64_t)sr.y * ldp + f;
@@ -312,15 +553,15 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const int4 *__restrict_
 #pragma unroll
     for (int k = 0; k < VEC; ++k) s[k] = 0.0;   // 0 + p0 == p0 exactly
     int q = 0;
-    for (; q + 4 <= sr.z; q += 4) {
-        double p[4][VEC];
+    for (; q + 8 <= sr.z; q += 8) {
+        double p[8][VEC];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             if (VEC == 2) { double2 tt = __ldcg(reinterpret_cast<const double2 *>(pp + (int64_t)(q + u) * ldp)); p[u][0] = tt.x; p[u][VEC - 1] = tt.y; }
             else p[u][0] = __ldcg(pp + (int64_t)(q + u) * ldp);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u)
 #pragma unroll
             for (int k = 0; k < VEC; ++k) s[k] = s[k] + p[u][k];
     }
@@ -372,6 +613,25 @@ static void wdot(const double *w, const double *A, int64_t lda, int64_t nrow, in
     IB_LAUNCHED();
 }
 
+// Launch a fix-up kernel so that its launch overlaps the tail of the SpMM kernel before it (programmatic dependent
+// launch); the kernel itself waits with griddepcontrol.wait before touching the partial sums.
+template <class... KArgs, class... Args>
+static void launch_dependent(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    IB_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+    IB_LAUNCHED();
+}
+
 void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY, int64_t ldy, bool force_conservation,
                cudaStream_t s)
 {
@@ -386,7 +646,7 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
 
     static const int variant = getenv("IB_SPMM_VARIANT") ? atoi(getenv("IB_SPMM_VARIANT")) : 0;   // 0 auto, 1 LDG, 2 TMA
     static const int want_bps = getenv("IB_SPMM_BPS") ? atoi(getenv("IB_SPMM_BPS")) : 4;            // TMA blocks per SM
-    bool done = false;
+    bool done = false, pair_done = false;
     if (vec2 && nvar >= 64 && variant != 1) {
         const int tw = std::min(nvar, TMA_MAX_TW);
         const int ntile = (nvar + tw - 1) / tw;
@@ -396,19 +656,33 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
             int dev = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-            IB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            IB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            IB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         }
-        const size_t stagebytes = (size_t)tw * 8 * TMA_ROWS;
+        const size_t stagebytes = (size_t)tw * 8 * TMA_ROWS + TMA_HDR;
         const size_t budget = (size_t)(max_smem + 1024) / want_bps - 1024 - 256;
         const int nstage = (int)std::min<size_t>(15, budget / stagebytes);
         if (nstage >= 2) {
             const size_t smem = 256 + (size_t)nstage * stagebytes;
             const int64_t slots = (int64_t)sm_count() * want_bps;
-            const int64_t per = std::max<int64_t>(1, cdiv(nunits, slots));
-            const int64_t nblk = std::max<int64_t>(1, cdiv(nunits, per));
-            SpmmArgs a{P.items.p, nunits, ntile, tw, nstage, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp};
-            spmm_tma_kernel<<<(unsigned)nblk, TMA_CONSUMERS + 32, smem, s>>>(a);
-            IB_LAUNCHED();
+            if (P.pair) {
+                const int64_t nun = P.pair_nitems * ntile;
+                const int64_t per = std::max<int64_t>(1, cdiv(nun, slots));
+                const int64_t nblk = std::max<int64_t>(1, cdiv(nun, per));
+                DBuf<double> pp((size_t)(2 * P.pair_nitems) * ldp, s);
+                SpmmArgs a{P.pair_items.p, nun, ntile, tw, nstage, W.rowptr.p, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, dY, ldy, pp.p, ldp};
+                spmm_tma_kernel<true><<<(unsigned)nblk, TMA_CONSUMERS + 32, smem, s>>>(a);
+                IB_LAUNCHED();
+                const int64_t tot = W.nrow * (int64_t)(nvar / 2);
+                launch_dependent(spmm_fixup_list_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.fx_ptr.p, P.fx_slot.p, W.nrow, pp.p, ldp, nvar, dY, ldy);
+                pair_done = true;
+            } else {
+                const int64_t per = std::max<int64_t>(1, cdiv(nunits, slots));
+                const int64_t nblk = std::max<int64_t>(1, cdiv(nunits, per));
+                SpmmArgs a{P.items.p, nunits, ntile, tw, nstage, W.rowptr.p, W.col.p, W.val.p, nullptr, dX, ldx, nvar, dY, ldy, partials.p, ldp};
+                spmm_tma_kernel<false><<<(unsigned)nblk, TMA_CONSUMERS + 32, smem, s>>>(a);
+                IB_LAUNCHED();
+            }
             done = true;
         }
     }
@@ -428,15 +702,14 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
             spmm_ldg_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp);
         IB_LAUNCHED();
     }
-    if (P.nsplit_rows > 0) {
+    if (P.nsplit_rows > 0 && !pair_done) {
         if (vec2) {
             int64_t tot = P.nsplit_rows * (nvar / 2);
-            spmm_fixup_kernel<2><<<(unsigned)cdiv(tot, 256), 256, 0, s>>>(P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy);
+            launch_dependent(spmm_fixup_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy);
         } else {
             int64_t tot = P.nsplit_rows * (int64_t)nvar;
-            spmm_fixup_kernel<1><<<(unsigned)cdiv(tot, 256), 256, 0, s>>>(P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy);
+            launch_dependent(spmm_fixup_kernel<1>, (unsigned)cdiv(tot, 256), 256, 0, s, P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy);
         }
-        IB_LAUNCHED();
     }
     if (!W.conservative && force_conservation) {
         DBuf<double> pa, pb, factor((size_t)nvar, s);

@@ -81,6 +81,15 @@ struct ApplyPlan {
     DBuf<int4> split_rows;   // (row, first_partial, nchunks, 0)
     int64_t npartials = 0;
     DBuf<int32_t> slot_srow; // partial slot -> split-row index
+    // pair-grouped column plan (matrices with <= 2 nonzeros per column, e.g. EvI): columns sharing the same pair
+    // of rows are chunked together so that each X row is read once and feeds both output rows
+    bool pair = false;
+    int64_t pair_nitems = 0;
+    DBuf<int4> pair_items;   // (r0, begin, end, first partial slot = 2*item) over the regrouped column stream
+    DBuf<int32_t> pcol;      // regrouped column ids
+    DBuf<double> pv0, pv1;   // values of the column's first / second nonzero (0 if none)
+    DBuf<int32_t> fx_ptr;    // [nrow+1] partial slots of each output row ...
+    DBuf<uint32_t> fx_slot;  // ... in a fixed order
 };
 
 // linear::Weighted_Eigen: CSR matrix (rows = output space) + weights + dims.

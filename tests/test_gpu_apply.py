@@ -30,7 +30,9 @@ def test_apply_cfg1(cfg1, spec, nvar):
 
 
 def test_apply_cfg2_bitexact_short_rows(cfg2):
-    """Rows with <= 32 nonzeros are accumulated in the oracle's order with mul-then-add: bit-identical."""
+    """Rows with <= 32 nonzeros are accumulated in the oracle's order with mul-then-add: bit-identical.
+    (EvI takes the pair-grouped column plan -- every X row read once for its two elevation classes -- whose rows are
+    sums of per-chunk partials: deterministic, but associated differently, so it is held to the 1e-12 gate only.)"""
     go, gg = make_oracle(cfg2), make_gpu(cfg2)
     em = cfg2["elevmask"][0]
     for spec in ("IvE", "IvA", "EvI", "AvI"):
@@ -41,7 +43,9 @@ def test_apply_cfg2_bitexact_short_rows(cfg2):
         assert np.all(np.abs(Yg - Yo) <= ref_tol(Wo, X)), spec
         rowlen = np.bincount(Wo.row, minlength=Wo.shape[0])
         short = rowlen <= 32
-        assert np.array_equal(Yg[:, short], Yo[:, short]), spec
+        if spec != "EvI":
+            assert np.array_equal(Yg[:, short], Yo[:, short]), spec
+        assert np.array_equal(Yg, Wg.apply(X)), spec + ": apply is not deterministic"
         # conservation: sum wM * (M f) == sum Mw * f     (test_conserv.py:174-205)
         lhs, rhs = (Yg * Wo.wM).sum(1), (X * Wo.Mw).sum(1)
         scale = (np.abs(X) * Wo.Mw).sum(1)
