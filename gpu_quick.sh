@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_apply.py -x -q -m gpu 2>&1 | tail -2 > gpurun_out/t.log
-python tools/bench_extra.py --skip-1km --out gpurun_out/extra_r1.json >> gpurun_out/t.log 2>&1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 4 --steps 300 --warmup 10 > gpurun_out/bench_n4.log 2>&1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 300 --warmup 10 > gpurun_out/bench_n2.log 2>&1

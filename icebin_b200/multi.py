@@ -52,8 +52,11 @@ def merge_reference(contribs, n_sparse, fill=np.nan):
 
 
 class SheetMerge:
-    """Per-rank merge state for a set of (unscaled) matrices whose rows live on the A or E grid.  All matrices share
-    ONE packed buffer, so a step costs a single all-reduce."""
+    """Per-rank merge state for a set of (unscaled) matrices whose rows live on the A or E grid.
+
+    begin(i, Y) packs the shared rows of result i and starts their all-reduce asynchronously (torch runs NCCL on its
+    own stream, ordered after the work already queued on the current stream), so the exchange of one result overlaps
+    the SpMM that produces the next; finish(Ys) waits and unpacks, dividing by the summed weights."""
 
     def __init__(self, spaces, nvar, device, group=None):
         """spaces: list of (n_sparse, Weighted)."""
@@ -61,38 +64,42 @@ class SheetMerge:
         self._lib, self._check = lib(), check
         self.nvar, self.group = nvar, group
         self.parts = []
-        off = 0
-        multi_rank = dist.is_initialized() and dist.get_world_size(group) > 1
+        self._multi = dist.is_initialized() and dist.get_world_size(group) > 1
         for n_sparse, W in spaces:
             shared_ids, loc, slot = plan_shared(W.dim(0), n_sparse, group)
-            part = dict(nrow=W.shape[0], nshared=len(shared_ids), off=off, shared_ids=shared_ids,
+            ns = len(shared_ids)
+            part = dict(nrow=W.shape[0], nshared=ns, shared_ids=shared_ids,
                         loc=torch.from_numpy(loc).to(device), slot=torch.from_numpy(slot).to(device),
-                        wlocal=torch.from_numpy(W.get_weights(0)).to(device))
-            off += len(shared_ids)
+                        wlocal=torch.from_numpy(W.get_weights(0)).to(device),
+                        buf=torch.zeros((max(ns, 1), nvar), dtype=torch.float64, device=device),
+                        wtot=torch.zeros(max(ns, 1), dtype=torch.float64, device=device), work=None)
+            # summed weights of the shared cells (they change only when the matrices are rebuilt)
+            if ns:
+                have = part["loc"] >= 0
+                part["wtot"][:ns][have] = part["wlocal"][part["loc"][have].long()]
+                if self._multi:
+                    dist.all_reduce(part["wtot"], group=group)
             self.parts.append(part)
-        self.nshared = off
-        self.buf = torch.zeros((max(off, 1), nvar), dtype=torch.float64, device=device)
-        # summed weights of the shared cells (they change only when the matrices are rebuilt)
-        self.wtot = torch.zeros(max(off, 1), dtype=torch.float64, device=device)
-        for p in self.parts:
-            have = p["loc"] >= 0
-            if p["nshared"]:
-                seg = self.wtot[p["off"]: p["off"] + p["nshared"]]
-                seg[have] = p["wlocal"][p["loc"][have].long()]
-        if off and multi_rank:
-            dist.all_reduce(self.wtot, group=group)
-        self._multi = multi_rank
+        self.nshared = sum(p["nshared"] for p in self.parts)
+
+    def begin(self, i, Y, stream):
+        p, nvar = self.parts[i], self.nvar
+        if p["nshared"]:
+            self._check(self._lib.ib_merge_pack_dev(Y.data_ptr(), nvar, nvar, p["loc"].data_ptr(), p["nshared"], p["buf"].data_ptr(), stream))
+            if self._multi:
+                p["work"] = dist.all_reduce(p["buf"], group=self.group, async_op=True)     # NCCL sum over NVLink
+
+    def finish(self, Ys, stream):
+        """Ys[i] [nrow_i, nvar] holds this sheet's unscaled sums; on return they hold the merged, scaled values."""
+        nvar = self.nvar
+        for p, Y in zip(self.parts, Ys):
+            if p["work"] is not None:
+                p["work"].wait()               # current stream waits for the collective
+                p["work"] = None
+            self._check(self._lib.ib_merge_unpack_dev(Y.data_ptr(), nvar, nvar, p["nrow"], p["slot"].data_ptr(), p["buf"].data_ptr(),
+                                                      p["wtot"].data_ptr(), p["wlocal"].data_ptr(), stream))
 
     def run(self, Ys, stream):
-        """Ys[i] [nrow_i, nvar] holds this sheet's unscaled sums; on return they hold the merged, scaled values."""
-        L, nvar = self._lib, self.nvar
-        for p, Y in zip(self.parts, Ys):
-            if p["nshared"]:
-                self._check(L.ib_merge_pack_dev(Y.data_ptr(), nvar, nvar, p["loc"].data_ptr(), p["nshared"],
-                                                self.buf.data_ptr() + p["off"] * nvar * 8, stream))
-        if self.nshared and self._multi:
-            dist.all_reduce(self.buf, group=self.group)             # NCCL sum over NVLink on the current stream
-        for p, Y in zip(self.parts, Ys):
-            self._check(L.ib_merge_unpack_dev(Y.data_ptr(), nvar, nvar, p["nrow"], p["slot"].data_ptr(),
-                                              self.buf.data_ptr() + p["off"] * nvar * 8, self.wtot.data_ptr() + p["off"] * 8,
-                                              p["wlocal"].data_ptr(), stream))
+        for i, Y in enumerate(Ys):
+            self.begin(i, Y, stream)
+        self.finish(Ys, stream)
