@@ -1,2 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 4 --steps 300 --warmup 10 > gpurun_out/bench_n4.log 2>&1
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 300 --warmup 10 > gpurun_out/bench_n2.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_apply.py tests/test_gpu_smooth.py -x -q -m gpu 2>&1 | tail -5 > gpurun_out/t.log
+timeout 120 python bench.py --steps 300 --warmup 10 --no-cpu-baseline 2>&1 | python tools/summ.py "bench fused" >> gpurun_out/t.log
+IB_SPMM_NOFUSE=1 timeout 120 python bench.py --steps 300 --warmup 10 --no-cpu-baseline 2>&1 | python tools/summ.py "bench nofuse" >> gpurun_out/t.log

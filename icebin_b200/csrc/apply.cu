@@ -21,6 +21,8 @@
 // oracle bit for bit; split rows differ only in association.
 //
 // Roofline: HBM.  Algorithmic bytes = 12*nnz + 4*(nrow+1) + 8*nvar*(ncol_touched + nrow)   (SURVEY 8d).
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "radix_sort.cuh"
@@ -353,6 +355,12 @@ struct SpmmArgs {
     int64_t ldy;
     double *partials;
     int64_t ldp;
+    // fused fix-up (cooperative launch only): 0 none, 1 split rows (contiguous partial slots), 2 slot lists
+    int fix_mode;
+    const int4 *split_rows;
+    int64_t nfix;                 // rows to finalise
+    const int32_t *fx_ptr;
+    const uint32_t *fx_slot;
 };
 
 // Shared-memory stage = [TMA_ROWS rows of X][header: TMA_ROWS values (+ TMA_ROWS second values)]; the producer
@@ -468,11 +476,57 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
                 if (lane == 0) mbar_arrive(empty + stage);
                 if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
             }
-            if (it.w >= 0 && active) {  // chunk: partial sum(s), combined in a fixed order by the fix-up kernel
+            if (it.w >= 0 && active) {  // chunk: partial sum(s), combined in a fixed order by the fix-up
                 reinterpret_cast<double2 *>(a.partials + (int64_t)it.w * a.ldp + f0)[t] = make_double2(a0, a1);
                 if (PAIR) reinterpret_cast<double2 *>(a.partials + (int64_t)(it.w + 1) * a.ldp + f0)[t] = make_double2(b0, b1);
             }
         }
+    }
+    if (a.fix_mode == 0) return;
+    // ---- fused fix-up: the grid is co-resident (cooperative launch), so one grid-wide barrier replaces a kernel
+    // boundary; afterwards every thread sums the partial rows of some (row, field pair) in the fixed slot order
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    const int nv2 = a.nvar / 2;
+    const int64_t total = a.nfix * nv2;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / nv2;
+        const int f = (int)(idx - r * nv2) * 2;
+        double2 acc = make_double2(0.0, 0.0);
+        int64_t orow;
+        if (a.fix_mode == 1) {
+            const int4 sr = a.split_rows[r];
+            orow = sr.x;
+            const double *pp = a.partials + (int64_t)sr.y * a.ldp + f;
+            int q = 0;
+            for (; q + 4 <= sr.z; q += 4) {
+                double2 p[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p[k] = __ldcg(reinterpret_cast<const double2 *>(pp + (int64_t)(q + k) * a.ldp));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { acc.x = acc.x + p[k].x; acc.y = acc.y + p[k].y; }
+            }
+            for (; q < sr.z; ++q) {
+                const double2 p = __ldcg(reinterpret_cast<const double2 *>(pp + (int64_t)q * a.ldp));
+                acc.x = acc.x + p.x; acc.y = acc.y + p.y;
+            }
+        } else {
+            orow = r;
+            const int b = a.fx_ptr[r], e = a.fx_ptr[r + 1];
+            int q = b;
+            for (; q + 4 <= e; q += 4) {
+                double2 p[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p[k] = __ldcg(reinterpret_cast<const double2 *>(a.partials + (int64_t)a.fx_slot[q + k] * a.ldp + f));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { acc.x = acc.x + p[k].x; acc.y = acc.y + p[k].y; }
+            }
+            for (; q < e; ++q) {
+                const double2 p = __ldcg(reinterpret_cast<const double2 *>(a.partials + (int64_t)a.fx_slot[q] * a.ldp + f));
+                acc.x = acc.x + p.x; acc.y = acc.y + p.y;
+            }
+        }
+        *reinterpret_cast<double2 *>(a.Y + orow * a.ldy + f) = acc;
     }
 }
 
@@ -664,24 +718,41 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         const int nstage = (int)std::min<size_t>(15, budget / stagebytes);
         if (nstage >= 2) {
             const size_t smem = 256 + (size_t)nstage * stagebytes;
-            const int64_t slots = (int64_t)sm_count() * want_bps;
-            if (P.pair) {
-                const int64_t nun = P.pair_nitems * ntile;
+            // measured on B200: the cooperative launch + grid barrier costs a little more than the PDL-launched fix-up kernel
+            static const bool fuse = getenv("IB_SPMM_FUSE") != nullptr;
+            // true residency (registers, shared memory) bounds the grid of a cooperative launch
+            int occ0 = 0, occ1 = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, spmm_tma_kernel<false>, TMA_CONSUMERS + 32, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, spmm_tma_kernel<true>, TMA_CONSUMERS + 32, smem);
+            auto launch = [&](auto kern, int occ, SpmmArgs a, int64_t nun, bool needs_fix) -> bool {
+                const int64_t slots = (int64_t)sm_count() * std::min(want_bps, std::max(occ, 1));
                 const int64_t per = std::max<int64_t>(1, cdiv(nun, slots));
                 const int64_t nblk = std::max<int64_t>(1, cdiv(nun, per));
-                DBuf<double> pp((size_t)(2 * P.pair_nitems) * ldp, s);
-                SpmmArgs a{P.pair_items.p, nun, ntile, tw, nstage, W.rowptr.p, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, dY, ldy, pp.p, ldp};
-                spmm_tma_kernel<true><<<(unsigned)nblk, TMA_CONSUMERS + 32, smem, s>>>(a);
+                if (needs_fix && fuse && occ >= 1 && nblk <= (int64_t)sm_count() * occ) {
+                    void *kargs[] = {&a};
+                    cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)nblk), dim3(TMA_CONSUMERS + 32), kargs, smem, s);
+                    if (e == cudaSuccess) { IB_LAUNCHED(); return true; }
+                    cudaGetLastError();      // fall through to the two-kernel path
+                }
+                a.fix_mode = 0;
+                kern<<<(unsigned)nblk, TMA_CONSUMERS + 32, smem, s>>>(a);
                 IB_LAUNCHED();
-                const int64_t tot = W.nrow * (int64_t)(nvar / 2);
-                launch_dependent(spmm_fixup_list_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.fx_ptr.p, P.fx_slot.p, W.nrow, pp.p, ldp, nvar, dY, ldy);
+                return false;
+            };
+            if (P.pair) {
+                const int64_t nun = P.pair_nitems * ntile;
+                DBuf<double> pp((size_t)(2 * P.pair_nitems) * ldp, s);
+                SpmmArgs a{P.pair_items.p, nun, ntile, tw, nstage, W.rowptr.p, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, dY, ldy, pp.p, ldp,
+                           2, nullptr, W.nrow, P.fx_ptr.p, P.fx_slot.p};
+                if (!launch(spmm_tma_kernel<true>, occ1, a, nun, true)) {
+                    const int64_t tot = W.nrow * (int64_t)(nvar / 2);
+                    launch_dependent(spmm_fixup_list_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.fx_ptr.p, P.fx_slot.p, W.nrow, pp.p, ldp, nvar, dY, ldy);
+                }
                 pair_done = true;
             } else {
-                const int64_t per = std::max<int64_t>(1, cdiv(nunits, slots));
-                const int64_t nblk = std::max<int64_t>(1, cdiv(nunits, per));
-                SpmmArgs a{P.items.p, nunits, ntile, tw, nstage, W.rowptr.p, W.col.p, W.val.p, nullptr, dX, ldx, nvar, dY, ldy, partials.p, ldp};
-                spmm_tma_kernel<false><<<(unsigned)nblk, TMA_CONSUMERS + 32, smem, s>>>(a);
-                IB_LAUNCHED();
+                SpmmArgs a{P.items.p, nunits, ntile, tw, nstage, W.rowptr.p, W.col.p, W.val.p, nullptr, dX, ldx, nvar, dY, ldy, partials.p, ldp,
+                           1, P.split_rows.p, P.nsplit_rows, nullptr, nullptr};
+                if (launch(spmm_tma_kernel<false>, occ0, a, nunits, P.nsplit_rows > 0)) pair_done = true;   // fix-up already done
             }
             done = true;
         }
