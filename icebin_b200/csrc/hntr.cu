@@ -14,6 +14,7 @@
 //
 // Roofline: HBM.  Algorithmic bytes = sizeof(Src)*nA [+ 8*nA with a weight array] + 8*nB   (SURVEY 8d).
 #include <cmath>
+#include <cstdlib>
 
 #include "scan.cuh"
 #include "types.cuh"
@@ -27,6 +28,13 @@ struct Hntr {
     std::vector<int> imin, imax, jmin, jmax;
     DBuf<double> d_sina, d_fmin, d_fmax, d_gmin, d_gmax, d_dxypB;
     DBuf<int> d_imin, d_imax, d_jmin, d_jmax;
+    bool nested_ew = false;     // every B cell is exactly imA/imB >= 8 whole A columns, starting at ib * imA/imB
+    // north-south fractions flattened per destination row: G of source row ja for destination row jb is
+    // gflat[goff[jb] + ja - jmin[jb]]; gsum[jb] = sum of them (hntr.hpp:215-219)
+    std::vector<double> gflat, gsum;
+    std::vector<int> goff;
+    DBuf<double> d_gflat, d_gsum;
+    DBuf<int> d_goff;
 };
 
 static std::vector<double> cell_areas(int im, int jm)   // HntrGrid::dxyp, hntr.cpp:34-52 (unit sphere)
@@ -110,6 +118,23 @@ Hntr *hntr_create(int imB, int jmB, double offiB, double dlatB, int imA, int jmA
         }
         h->jmax[jmB - 1] = jmA;
     }
+    h->goff.assign(jmB + 1, 0);
+    h->gsum.assign(jmB, 0.0);
+    for (int jb = 0; jb < jmB; ++jb) {
+        h->goff[jb] = (int)h->gflat.size();
+        for (int ja = h->jmin[jb]; ja <= h->jmax[jb]; ++ja) {
+            double G = h->sina[ja] - h->sina[ja - 1];
+            if (ja == h->jmin[jb]) G -= h->gmin[jb];
+            if (ja == h->jmax[jb]) G -= h->gmax[jb];
+            h->gflat.push_back(G);
+            h->gsum[jb] += G;
+        }
+    }
+    h->goff[jmB] = (int)h->gflat.size();
+    h->nested_ew = (imA % imB == 0) && (imA % 8 == 0) && (imA / imB >= 8);
+    for (int ib = 0; ib < imB && h->nested_ew; ++ib)
+        h->nested_ew = h->fmin[ib] == 0 && h->fmax[ib] == 0 && (h->imin[ib] - 1) % imA == ib * (imA / imB) &&
+                       h->imax[ib] - h->imin[ib] + 1 == imA / imB;
     return h.release();
 }
 
@@ -118,6 +143,7 @@ static void hntr_upload(Hntr &h, cudaStream_t s)
     if (h.d_sina.n) return;
     auto up = [&](auto &d, auto const &v) { d.alloc(v.size(), s); d.upload(v.data(), v.size()); };
     up(h.d_sina, h.sina); up(h.d_fmin, h.fmin); up(h.d_fmax, h.fmax); up(h.d_gmin, h.gmin); up(h.d_gmax, h.gmax);
+    up(h.d_gflat, h.gflat); up(h.d_gsum, h.gsum); up(h.d_goff, h.goff);
     up(h.d_dxypB, h.dxypB); up(h.d_imin, h.imin); up(h.d_imax, h.imax); up(h.d_jmin, h.jmin); up(h.d_jmax, h.jmax);
     IB_CUDA(cudaStreamSynchronize(s));
 }
@@ -285,6 +311,83 @@ __global__ void __launch_bounds__(256) hntr_polar_kernel(double *__restrict__ B,
     for (int i = threadIdx.x; i < imB; i += blockDim.x) row[i] = mean;
 }
 
+// ---- fast path: int16 source, constant weight, east-west exactly nested (ETOPO1 1' -> any ModelE grid) --------
+// With F == 1 everywhere the inner sum over a destination cell's source columns is an INTEGER sum, so a thread that
+// owns 8 consecutive int16 columns folds each source row with 4 two-way integer dot products (IDP.2A) instead of
+// 8 int->fp64 conversions + 8 DFMAs: ~2 instead of ~9.5 instructions per element, which is what lets the kernel run
+// at memory speed.  A thread's 8 columns touch at most two destination cells (cell width >= 8): elements k < split
+// go to the first (acc0), the rest to the second (acc1).  Integer row sums are exact; only G * sum is rounded.
+__device__ __forceinline__ double i32_to_f64(int x)      // exact, without the XU conversion pipe
+{
+    return __hiloint2double(0x43300000, x ^ 0x80000000) - 4503601774854144.0;      // 2^52 + 2^31
+}
+template <int UNR>
+__global__ void __launch_bounds__(128, 12) hntr_i16_nested_kernel(const int16_t *__restrict__ A, int imA, int cols_per_b,
+                                                                  const int *__restrict__ jmin, const int *__restrict__ jmax,
+                                                                  const double *__restrict__ gflat, const int *__restrict__ goff,
+                                                                  double wconst, double *__restrict__ P)
+{
+    // blockIdx.z splits the source rows of a destination row into gridDim.z interleaved parts (more CTAs when the
+    // destination grid has few rows); part z writes its own slice of P and stage 2 adds the parts in order
+    const int jb = blockIdx.y;
+    const int nvec = imA >> 3;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvec) return;
+    const int c0 = v << 3;
+    const int split = min(8, (c0 / cols_per_b + 1) * cols_per_b - c0);      // elements of this vector in its first cell
+    unsigned m[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m[q] = (2 * q + 1 < split) ? 0xffffffffu : ((2 * q < split) ? 0x0000ffffu : 0u);
+    const int jlo = jmin[jb], jhi = jmax[jb];
+    const double *g = gflat + goff[jb] - jlo;
+    double acc0 = 0.0, acc1 = 0.0;
+    const int4 *src = reinterpret_cast<const int4 *>(A) + v;
+#pragma unroll UNR
+    for (int ja = jlo + (int)blockIdx.z; ja <= jhi; ja += (int)gridDim.z) {
+        const int4 r = __ldg(src + (int64_t)(ja - 1) * nvec);
+        const double gw = __ldg(g + ja) * wconst;
+        const int w[4] = {r.x, r.y, r.z, r.w};
+        int s_all = 0, s_lo = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            s_all = __dp2a_lo(w[q], 0x0101, s_all);
+            s_lo = __dp2a_lo((int)((unsigned)w[q] & m[q]), 0x0101, s_lo);
+        }
+        acc0 += gw * i32_to_f64(s_lo);
+        acc1 += gw * i32_to_f64(s_all - s_lo);
+    }
+    reinterpret_cast<double2 *>(P)[((int64_t)blockIdx.z * gridDim.y + jb) * nvec + v] = make_double2(acc0, acc1);
+}
+
+// a group of L lanes (L = 1..32, power of two) per destination cell: add, in a fixed order, the per-vector sums that
+// belong to it; weight = cols * w * sum_JA G
+__global__ void __launch_bounds__(256) hntr_rows_nested_kernel(const double *__restrict__ P, int nz, int imA, int imB, int jmB, int cols_per_b,
+                                                               int L, const double *__restrict__ gsum, double wconst, double datmis,
+                                                               double *__restrict__ B)
+{
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % L;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t cell = t / L;
+    const int64_t ncell = (int64_t)imB * jmB;
+    const bool live = cell < ncell;
+    const int jb = live ? (int)(cell / imB) : 0, ib = live ? (int)(cell - (int64_t)jb * imB) : 0;
+    const int nvec = imA >> 3;
+    const int v_lo = (ib * cols_per_b) >> 3, v_hi = (ib * cols_per_b + cols_per_b - 1) >> 3;
+    const int nv = v_hi - v_lo + 1;
+    double vsum = 0.0;
+    if (live)
+        for (int k = sub; k < nv * nz; k += L) {
+            const int z = k / nv, v = v_lo + (k - z * nv);
+            const double2 tt = reinterpret_cast<const double2 *>(P)[((int64_t)z * jmB + jb) * nvec + v];
+            vsum += ((v << 3) / cols_per_b == ib) ? tt.x : tt.y;
+        }
+    for (int d = L >> 1; d > 0; d >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, d);
+    if (!live || sub != 0) return;
+    const double wsum = (gsum[jb] * wconst) * (double)cols_per_b;
+    B[cell] = (wsum == 0) ? datmis : vsum / wsum;
+}
+
 template <class SrcT, int CPT>
 static void launch_cols(Hntr &h, const SrcT *A, const double *W, double wtm, double wtb, double *S, double *T, cudaStream_t s)
 {
@@ -302,8 +405,30 @@ void hntr_regrid_dev(Hntr &h, const double *d_wta, double wtm, double wtb, const
 {
     ensure_device();
     hntr_upload(h, s);
-    DBuf<double> S((size_t)h.jmB * h.imA, s), T((size_t)h.jmB * h.imA, s);
     const bool al16 = ((uintptr_t)d_src % 16 == 0) && (d_wta == nullptr || (uintptr_t)d_wta % 16 == 0);
+    const int64_t ncell = (int64_t)h.imB * h.jmB;
+    if (src_dtype == IB_SRC_I16 && d_wta == nullptr && al16 && h.nested_ew && !getenv("IB_HNTR_GENERIC")) {
+        const int nvec = h.imA / 8, cpb = h.imA / h.imB;
+        const double wconst = wtm * 1.0 + wtb;
+        const int64_t xb = cdiv(nvec, 128);
+        const int nz = (int)std::min<int64_t>(8, std::max<int64_t>(1, cdiv(3500, xb * h.jmB)));
+        DBuf<double> P((size_t)nz * h.jmB * nvec * 2, s);
+        dim3 grid((unsigned)xb, (unsigned)h.jmB, (unsigned)nz);
+        hntr_i16_nested_kernel<4><<<grid, 128, 0, s>>>((const int16_t *)d_src, h.imA, cpb, h.d_jmin.p, h.d_jmax.p, h.d_gflat.p, h.d_goff.p,
+                                                       wconst, P.p);
+        IB_LAUNCHED();
+        const int work = ((cpb + 7) / 8 + 1) * nz;      // per-vector sums a destination cell adds up
+        int L = 1;
+        while (L < 32 && 2 * L <= work) L <<= 1;
+        hntr_rows_nested_kernel<<<(unsigned)cdiv(ncell * L, 256), 256, 0, s>>>(P.p, nz, h.imA, h.imB, h.jmB, cpb, L, h.d_gsum.p, wconst, h.datmis, d_dst);
+        IB_LAUNCHED();
+        if (mean_polar) {
+            hntr_polar_kernel<<<h.jmB > 1 ? 2 : 1, 256, 0, s>>>(d_dst, h.imB, h.jmB, h.datmis);
+            IB_LAUNCHED();
+        }
+        return;
+    }
+    DBuf<double> S((size_t)h.jmB * h.imA, s), T((size_t)h.jmB * h.imA, s);
     if (src_dtype == IB_SRC_I16) {
         if (al16 && h.imA % 8 == 0) launch_cols<int16_t, 8>(h, (const int16_t *)d_src, d_wta, wtm, wtb, S.p, T.p, s);
         else launch_cols<int16_t, 1>(h, (const int16_t *)d_src, d_wta, wtm, wtb, S.p, T.p, s);
@@ -313,7 +438,6 @@ void hntr_regrid_dev(Hntr &h, const double *d_wta, double wtm, double wtb, const
     } else {
         fail(IB_ERR_ARG, "hntr_regrid: unknown source dtype %d", src_dtype);
     }
-    const int64_t ncell = (int64_t)h.imB * h.jmB;
     hntr_rows_kernel<<<(unsigned)cdiv(ncell * 32, 256), 256, 0, s>>>(S.p, T.p, h.imA, h.imB, h.jmB, h.d_imin.p, h.d_imax.p, h.d_fmin.p,
                                                                     h.d_fmax.p, h.datmis, d_dst);
     IB_LAUNCHED();
