@@ -150,6 +150,11 @@ class Weighted:
         check(lib().ib_w_apply_dev(self._h, vp(dX_ptr), ldx, nvar, vp(dY_ptr), ldy, int(force_conservation),
                                    vp(stream) if stream else None))
 
+    def apply_rows_dev(self, dX_ptr, ldx, nvar, dY_ptr, ldy, row_begin, row_end, stream=0):
+        """Row-block shard of apply_dev: only output rows [row_begin, row_end) (multiples of 32) are computed."""
+        check(lib().ib_w_apply_rows_dev(self._h, vp(dX_ptr), ldx, nvar, vp(dY_ptr), ldy, row_begin, row_end,
+                                        vp(stream) if stream else None))
+
     def apply_M(self, A_s, fill=np.nan, force_conservation=True):
         """Sparse-indexed apply (matrix_formats.rst:150-165).  A_s: [sparse_extent(A)] or [nvar, sparse_extent(A)]."""
         A = _c(A_s, np.float64)

@@ -355,6 +355,7 @@ struct SpmmArgs {
     int64_t ldy;
     double *partials;
     int64_t ldp;
+    int row_lo, row_hi;           // only items whose first row lies in [row_lo, row_hi) are processed (row-block sharding)
     // fused fix-up (cooperative launch only): 0 none, 1 split rows (contiguous partial slots), 2 slot lists
     int fix_mode;
     const int4 *split_rows;
@@ -394,6 +395,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
             const int tile = (int)(u - item * a.ntile);
             const int4 it = it_next;
             if (u + gridDim.x < a.nunits) it_next = a.items[(u + gridDim.x) / a.ntile];
+            if (it.x < a.row_lo || it.x >= a.row_hi) continue;
             const int f0 = tile * a.tw;
             const uint32_t tb = (uint32_t)min(a.tw, a.nvar - f0) * 8u;
             for (int j = it.y; j < it.z; j += TMA_ROWS) {
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
             const int tile = (int)(u - item * a.ntile);
             const int4 it = it_next;
             if (u + gridDim.x < a.nunits) it_next = a.items[(u + gridDim.x) / a.ntile];
+            if (it.x < a.row_lo || it.x >= a.row_hi) continue;
             const int f0 = tile * a.tw;
             const bool active = 2 * t < min(a.tw, a.nvar - f0);
             const int nrows = it.w < 0 ? -it.w : 0;
@@ -497,6 +500,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
         if (a.fix_mode == 1) {
             const int4 sr = a.split_rows[r];
             orow = sr.x;
+            if (sr.x < a.row_lo || sr.x >= a.row_hi) continue;
             const double *pp = a.partials + (int64_t)sr.y * a.ldp + f;
             int q = 0;
             for (; q + 4 <= sr.z; q += 4) {
@@ -537,7 +541,7 @@ __global__ void __launch_bounds__(256) spmm_ldg_kernel(const int4 *__restrict__ 
                                                        const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                                        const double *__restrict__ val, const double *__restrict__ X, int64_t ldx,
                                                        int nvar, double *__restrict__ Y, int64_t ldy, double *__restrict__ partials,
-                                                       int64_t ldp)
+                                                       int64_t ldp, int row_lo, int row_hi)
 {
     const int lane = threadIdx.x & 31;
     const int G = 32 / L;
@@ -550,6 +554,7 @@ __global__ void __launch_bounds__(256) spmm_ldg_kernel(const int4 *__restrict__ 
         const int f0 = (tile * L + fl) * VEC;
         if (f0 >= nvar) continue;
         const int4 it = items[item];
+        if (it.x < row_lo || it.x >= row_hi) continue;
         const int nrows = it.w < 0 ? -it.w : 1;
         for (int rr = 0; rr < nrows; ++rr) {
             const int jb = it.w < 0 ? __ldg(rowptr + it.x + rr) : it.y;
@@ -593,7 +598,7 @@ __global__ void __launch_bounds__(256) spmm_ldg_kernel(const int4 *__restrict__ 
 template <int VEC>
 __global__ void __launch_bounds__(256) spmm_fixup_kernel(const int4 *__restrict__ split_rows, int64_t nsplit,
                                                          const double *__restrict__ partials, int64_t ldp, int nvar,
-                                                         double *__restrict__ Y, int64_t ldy)
+                                                         double *__restrict__ Y, int64_t ldy, int row_lo, int row_hi)
 {
     const int nv = nvar / VEC;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -602,6 +607,7 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const int4 *__restrict_
     asm volatile("griddepcontrol.wait;" ::: "memory");      // launched with programmatic stream serialization
     if (r >= nsplit) return;
     const int4 sr = split_rows[r];
+    if (sr.x < row_lo || sr.x >= row_hi) return;
     const double *pp = partials + (int64_t)sr.y * ldp + f;
     double s[VEC];
 #pragma unroll
@@ -687,10 +693,22 @@ static void launch_dependent(void (*kern)(KArgs...), unsigned grid, unsigned blo
 }
 
 void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY, int64_t ldy, bool force_conservation,
-               cudaStream_t s)
+               cudaStream_t s, int64_t row_begin, int64_t row_end)
 {
     ensure_device();
     if (nvar <= 0 || W.nrow == 0) return;
+    if (row_end < 0) row_end = W.nrow;
+    const bool ranged = !(row_begin == 0 && row_end == W.nrow);
+    if (ranged) {
+        // row-block sharding (output rows split across GPUs, inputs replicated): groups of short rows never cross a
+        // multiple of GROUP_ROWS, so blocks aligned to it own whole items
+        if (row_begin < 0 || row_end > W.nrow || row_begin > row_end || row_begin % GROUP_ROWS || (row_end % GROUP_ROWS && row_end != W.nrow))
+            fail(IB_ERR_ARG, "apply: row block [%ld, %ld) must be aligned to %d rows", (long)row_begin, (long)row_end, GROUP_ROWS);
+        if (!W.conservative && force_conservation)
+            fail(IB_ERR_ARG, "apply: the conservation correction needs all rows; apply row blocks with force_conservation=0");
+        if (row_begin == row_end) return;
+    }
+    const int rlo = (int)row_begin, rhi = (int)row_end;
     if (ldx < nvar || ldy < nvar) fail(IB_ERR_ARG, "apply: leading dimension smaller than nvar");
     make_plan(W, s);
     ApplyPlan &P = W.plan;
@@ -739,11 +757,11 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
                 IB_LAUNCHED();
                 return false;
             };
-            if (P.pair) {
+            if (P.pair && !ranged) {
                 const int64_t nun = P.pair_nitems * ntile;
                 DBuf<double> pp((size_t)(2 * P.pair_nitems) * ldp, s);
                 SpmmArgs a{P.pair_items.p, nun, ntile, tw, nstage, W.rowptr.p, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, dY, ldy, pp.p, ldp,
-                           2, nullptr, W.nrow, P.fx_ptr.p, P.fx_slot.p};
+                           0, 0x7fffffff, 2, nullptr, W.nrow, P.fx_ptr.p, P.fx_slot.p};
                 if (!launch(spmm_tma_kernel<true>, occ1, a, nun, true)) {
                     const int64_t tot = W.nrow * (int64_t)(nvar / 2);
                     launch_dependent(spmm_fixup_list_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.fx_ptr.p, P.fx_slot.p, W.nrow, pp.p, ldp, nvar, dY, ldy);
@@ -751,7 +769,7 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
                 pair_done = true;
             } else {
                 SpmmArgs a{P.items.p, nunits, ntile, tw, nstage, W.rowptr.p, W.col.p, W.val.p, nullptr, dX, ldx, nvar, dY, ldy, partials.p, ldp,
-                           1, P.split_rows.p, P.nsplit_rows, nullptr, nullptr};
+                           rlo, rhi, 1, P.split_rows.p, P.nsplit_rows, nullptr, nullptr};
                 if (launch(spmm_tma_kernel<false>, occ0, a, nunits, P.nsplit_rows > 0)) pair_done = true;   // fix-up already done
             }
             done = true;
@@ -768,18 +786,18 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         int64_t blocks = std::min<int64_t>(cdiv(cdiv(nunits, G), 8), (int64_t)sm_count() * 8);
         if (blocks < 1) blocks = 1;
         if (VEC == 2)
-            spmm_ldg_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp);
+            spmm_ldg_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp, rlo, rhi);
         else
-            spmm_ldg_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp);
+            spmm_ldg_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp, rlo, rhi);
         IB_LAUNCHED();
     }
     if (P.nsplit_rows > 0 && !pair_done) {
         if (vec2) {
             int64_t tot = P.nsplit_rows * (nvar / 2);
-            launch_dependent(spmm_fixup_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy);
+            launch_dependent(spmm_fixup_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy, rlo, rhi);
         } else {
             int64_t tot = P.nsplit_rows * (int64_t)nvar;
-            launch_dependent(spmm_fixup_kernel<1>, (unsigned)cdiv(tot, 256), 256, 0, s, P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy);
+            launch_dependent(spmm_fixup_kernel<1>, (unsigned)cdiv(tot, 256), 256, 0, s, P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy, rlo, rhi);
         }
     }
     if (!W.conservative && force_conservation) {

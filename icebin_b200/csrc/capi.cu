@@ -458,6 +458,16 @@ int ib_w_apply_dev(const ib_weighted *W, const double *dX, int64_t ldx, int32_t 
     IB_CATCH
 }
 
+int ib_w_apply_rows_dev(const ib_weighted *W, const double *dX, int64_t ldx, int32_t nvar, double *dY, int64_t ldy, int64_t row_begin,
+                        int64_t row_end, void *stream)
+{
+    IB_TRY
+    if (!W || !dX || !dY) fail(IB_ERR_ARG, "ib_w_apply_rows_dev: bad argument");
+    apply_dev(*W->w, dX, ldx, nvar, dY, ldy, false, stream ? (cudaStream_t)stream : W->w->stream, row_begin, row_end);
+    return IB_OK;
+    IB_CATCH
+}
+
 int ib_w_apply(const ib_weighted *W, const double *X, int64_t ldx, int32_t nvar, double *Y, int64_t ldy, int layout,
                int force_conservation)
 {

@@ -125,6 +125,11 @@ int ib_w_apply(const ib_weighted *, const double *X, int64_t ldx, int32_t nvar, 
                int force_conservation);
 int ib_w_apply_dev(const ib_weighted *, const double *dX, int64_t ldx, int32_t nvar, double *dY, int64_t ldy,
                    int force_conservation, void *stream);          /* cell-major only */
+/* Row-block sharding of an apply across GPUs (north star: "output row blocks of the I/E grids are split across GPUs with
+ * input fields replicated" -- no collective): computes only output rows [row_begin, row_end) of dY = M dX.
+ * row_begin and row_end must be multiples of 32 (row_end may also be nrow).  No conservation correction. */
+int ib_w_apply_rows_dev(const ib_weighted *, const double *dX, int64_t ldx, int32_t nvar, double *dY, int64_t ldy,
+                        int64_t row_begin, int64_t row_end, void *stream);
 /* Python apply_M(A_s, fill, force_conservation): sparse-indexed in and out   matrix_formats.rst:150-165
  * A_s: [nvar][sparse_extent(dim1)] field-major, B_s: [nvar][sparse_extent(dim0)] */
 int ib_w_apply_M(const ib_weighted *, const double *A_s, int32_t nvar, double *B_s, double fill,

@@ -83,3 +83,31 @@ def test_constant_roundtrips(cfg2):
         one = np.ones((1, M[a].shape[1]))
         back = M[b].apply(M[a].apply(one))
         assert np.abs(back - 1).max() < 1e-13, (a, b)
+
+
+@pytest.mark.parametrize("spec,nvar", [("IvE", 64), ("AvI", 64), ("EvI", 6), ("IvA", 512)])
+def test_row_block_sharding(cfg2, spec, nvar):
+    """Output row blocks computed separately (as N GPUs would, inputs replicated, no collective) reproduce the
+    full apply bit for bit."""
+    import torch
+    gg = make_gpu(cfg2)
+    M = gg.regrid_matrices(cfg2["sheets"][0].name, cfg2["elevmask"][0], scale=True, correctA=True).matrix(spec)
+    dev = torch.device("cuda")
+    X = torch.rand((M.shape[1], nvar), dtype=torch.float64, device=dev)
+    Yfull = torch.empty((M.shape[0], nvar), dtype=torch.float64, device=dev)
+    if spec == "EvI":
+        M.apply_rows_dev(X.data_ptr(), nvar, nvar, Yfull.data_ptr(), nvar, 0, M.shape[0])      # same (row-chunk) plan
+    else:
+        M.apply_dev(X.data_ptr(), nvar, nvar, Yfull.data_ptr(), nvar)
+    Y = torch.full((M.shape[0], nvar), float("nan"), dtype=torch.float64, device=dev)
+    nparts = 4
+    per = -(-M.shape[0] // nparts)
+    per = -(-per // 32) * 32
+    for k in range(nparts):
+        lo, hi = min(k * per, M.shape[0]), min((k + 1) * per, M.shape[0])
+        M.apply_rows_dev(X.data_ptr(), nvar, nvar, Y.data_ptr(), nvar, lo, hi)
+    torch.cuda.synchronize()
+    assert torch.equal(Y, Yfull)
+    from icebin_b200 import api
+    with pytest.raises(api.IceBinError):
+        M.apply_rows_dev(X.data_ptr(), nvar, nvar, Y.data_ptr(), nvar, 5, 64)
