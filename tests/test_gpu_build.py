@@ -112,3 +112,67 @@ def test_all_masked(cfg1):
     em = np.full(sh.nI, np.nan)
     W = gg.regrid_matrices(sh.name, em).matrix("EvI")
     assert W.shape == (0, 0) and W.nnz == 0
+
+
+def _shuffled_with_duplicates(cfg, seed=3):
+    """The same grids with the exchange cells in RANDOM order (upstream's order is implementation-defined,
+    SURVEY Appendix B.9) and 5 % of them split into two records of half the area (duplicate (iA, iI) pairs, which
+    setFromTriplets sums)."""
+    import copy
+    rng = np.random.default_rng(seed)
+    c = dict(cfg)
+    sh = copy.copy(cfg["sheets"][0])
+    n = sh.nX
+    dup = rng.choice(n, n // 20, replace=False)
+    ij = np.concatenate([sh.ex_ij, sh.ex_ij[dup]])
+    area = sh.ex_area.copy()
+    area[dup] *= 0.5
+    area = np.concatenate([area, area[dup]])
+    perm = rng.permutation(len(area))
+    sh.ex_ij, sh.ex_area = np.ascontiguousarray(ij[perm]), np.ascontiguousarray(area[perm])
+    c["sheets"] = [sh]
+    return c
+
+
+@pytest.mark.parametrize("spec", SIX + ["EvX", "XvA"])
+def test_arbitrary_order_and_duplicate_cells(cfg1, spec):
+    cfg = _shuffled_with_duplicates(cfg1)
+    go, gg = make_oracle(cfg), make_gpu(cfg)
+    em = cfg["elevmask"][0]
+    for scale, cA in ((True, True), (False, False)):
+        Wo = go.matrix(0, em, spec, scale=scale, correctA=cA)
+        Wg = gg.regrid_matrices(cfg["sheets"][0].name, em, scale=scale, correctA=cA).matrix(spec)
+        exact = assert_same(Wg, Wo, "%s shuffled scale=%d correctA=%d" % (spec, scale, cA))
+        assert exact, spec + ": duplicates must be summed in emission order (stable sort) to stay bit-identical"
+    # and the result is the same operator as with the tidy grid, up to the dense renumbering
+    if spec in SIX:
+        W0 = make_oracle(cfg1).matrix(0, em, spec, scale=True, correctA=True)
+        W1 = go.matrix(0, em, spec, scale=True, correctA=True)
+        import scipy.sparse as sp
+        A0 = sp.coo_matrix((W0.val, (W0.dims[0][W0.row], W0.dims[1][W0.col])), shape=W0.sparse_extent).tocsr()
+        A1 = sp.coo_matrix((W1.val, (W1.dims[0][W1.row], W1.dims[1][W1.col])), shape=W1.sparse_extent).tocsr()
+        assert abs(A0 - A1).max() <= 1e-12 * abs(A0).max()
+
+
+def test_single_elevation_class_is_fatal(cfg1):
+    """linterp_1d_b with one height point always runs off the top (IceRegridder_L0.cpp:82-85)."""
+    from icebin_b200 import api
+    c = dict(cfg1); c["hcdefs"] = np.array([0.0])
+    gg = make_gpu(c)
+    with pytest.raises(api.IceBinError) as e:
+        gg.regrid_matrices(c["sheets"][0].name, c["elevmask"][0]).matrix("EvI")
+    assert e.value.code == -3
+    gg.regrid_matrices(c["sheets"][0].name, c["elevmask"][0]).matrix("IvA")
+
+
+def test_elevation_on_class_boundaries(cfg1):
+    """Elevations exactly on a height point give one zero weight, which upstream drops (whps != 0, L0.cpp:133,139)."""
+    go, gg = make_oracle(cfg1), make_gpu(cfg1)
+    em = cfg1["elevmask"][0].copy()
+    ok = np.flatnonzero(~np.isnan(em))
+    em[ok[::3]] = cfg1["hcdefs"][3]          # exactly on a point
+    em[ok[1::3]] = -25.0                     # negative: clamped to 0 (L0.cpp:123)
+    for spec in ("EvI", "IvE", "EvA", "AvE"):
+        Wo = go.matrix(0, em, spec, scale=True, correctA=True)
+        Wg = gg.regrid_matrices(cfg1["sheets"][0].name, em, scale=True, correctA=True).matrix(spec)
+        assert assert_same(Wg, Wo, spec)
