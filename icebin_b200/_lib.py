@@ -53,6 +53,8 @@ SIGNATURES = {
     "ib_w_dev_ptrs": (C.c_int, [vp, PP, PP, PP, PP, PP]),
     "ib_w_apply": (C.c_int, [vp, vp, i64, i32, vp, i64, C.c_int, C.c_int]),
     "ib_w_apply_dev": (C.c_int, [vp, vp, i64, i32, vp, i64, C.c_int, vp]),
+    "ib_w_apply_many_dev": (C.c_int, [i32, vp, vp, i64, i32, vp, vp, C.c_int, vp]),
+    "ib_w_apply_many": (C.c_int, [i32, vp, vp, i64, i32, vp, vp, C.c_int, C.c_int]),
     "ib_w_apply_rows_dev": (C.c_int, [vp, vp, i64, i32, vp, i64, i64, i64, vp]),
     "ib_w_apply_M": (C.c_int, [vp, vp, i32, vp, f64, C.c_int]),
     "ib_w_apply_weight": (C.c_int, [vp, C.c_int, vp, i32, vp]),

@@ -14,7 +14,7 @@ import numpy as np
 from ._lib import IceBinError, check, lib, vp
 
 __all__ = ["GCMRegridder", "RegridMatrices", "Weighted", "SparseSet", "HntrSpec", "Hntr", "IceBinError",
-           "coo_matvec", "multivec_to_dense", "device_count", "launch_count"]
+           "coo_matvec", "multivec_to_dense", "device_count", "launch_count", "apply_many", "apply_many_dev"]
 
 
 def _p(a):
@@ -187,6 +187,37 @@ class Weighted:
                 self._h = None
         except Exception:      # interpreter shutdown: the loader module may already be gone
             pass
+
+
+def apply_many_dev(mats, dX_ptr, ldx, nvar, dY_ptrs, ldys, force_conservation=True, stream=0):
+    """Apply several matrices to the SAME device-resident input fields concurrently (IceCoupler.cpp:445-446 applies
+    EvI and AvI to one ice_ovalsI).  dY_ptrs[i] receives mats[i] @ X."""
+    n = len(mats)
+    Wp = (vp * n)(*[m._h for m in mats])
+    Yp = (vp * n)(*[vp(p) for p in dY_ptrs])
+    ld = (C.c_int64 * n)(*ldys)
+    check(lib().ib_w_apply_many_dev(n, Wp, vp(dX_ptr), ldx, nvar, Yp, ld, int(force_conservation), vp(stream) if stream else None))
+
+
+def apply_many(mats, X, force_conservation=True, layout="cell"):
+    """Host-buffer form: X is uploaded once.  layout='cell': X [ncol, nvar] -> list of [nrow_i, nvar];
+    layout='field': X [nvar, ncol] -> list of [nvar, nrow_i]."""
+    X = _c(np.atleast_2d(X), np.float64)
+    n = len(mats)
+    if layout == "cell":
+        nvar = X.shape[1]
+        Ys = [np.zeros((m.shape[0], nvar)) for m in mats]
+        ld = (C.c_int64 * n)(*[nvar] * n)
+        ldx, lay = nvar, 0
+    else:
+        nvar = X.shape[0]
+        Ys = [np.zeros((nvar, m.shape[0])) for m in mats]
+        ld = (C.c_int64 * n)(*[max(1, m.shape[0]) for m in mats])
+        ldx, lay = X.shape[1], 1
+    Wp = (vp * n)(*[m._h for m in mats])
+    Yp = (vp * n)(*[y.ctypes.data_as(vp) for y in Ys])
+    check(lib().ib_w_apply_many(n, Wp, _p(X), ldx, nvar, Yp, ld, lay, int(force_conservation)))
+    return Ys
 
 
 class RegridMatrices:

@@ -762,7 +762,8 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
                 DBuf<double> pp((size_t)(2 * P.pair_nitems) * ldp, s);
                 SpmmArgs a{P.pair_items.p, nun, ntile, tw, nstage, W.rowptr.p, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, dY, ldy, pp.p, ldp,
                            0, 0x7fffffff, 2, nullptr, W.nrow, P.fx_ptr.p, P.fx_slot.p};
-                if (!launch(spmm_tma_kernel<true>, occ1, a, nun, true)) {
+                static const bool skipfix = getenv("IB_SPMM_SKIPFIX") != nullptr;      // timing experiments only
+                if (!launch(spmm_tma_kernel<true>, occ1, a, nun, true) && !skipfix) {
                     const int64_t tot = W.nrow * (int64_t)(nvar / 2);
                     launch_dependent(spmm_fixup_list_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.fx_ptr.p, P.fx_slot.p, W.nrow, pp.p, ldp, nvar, dY, ldy);
                 }
@@ -791,7 +792,7 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
             spmm_ldg_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp, rlo, rhi);
         IB_LAUNCHED();
     }
-    if (P.nsplit_rows > 0 && !pair_done) {
+    if (P.nsplit_rows > 0 && !pair_done && !getenv("IB_SPMM_SKIPFIX")) {
         if (vec2) {
             int64_t tot = P.nsplit_rows * (nvar / 2);
             launch_dependent(spmm_fixup_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy, rlo, rhi);

@@ -458,6 +458,98 @@ int ib_w_apply_dev(const ib_weighted *W, const double *dX, int64_t ldx, int32_t 
     IB_CATCH
 }
 
+// fork/join helper for independent applies
+static void apply_many(int nmat, const ib_weighted *const *W, const double *dX, int64_t ldx, int nvar, double *const *dY,
+                       const int64_t *ldy, bool force, cudaStream_t s)
+{
+    static std::mutex mu;
+    static cudaStream_t aux[64][7] = {};
+    static cudaEvent_t fork_ev[64] = {}, join_ev[64][7] = {};
+    int dev = 0;
+    IB_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!fork_ev[dev]) {
+            IB_CUDA(cudaEventCreateWithFlags(&fork_ev[dev], cudaEventDisableTiming));
+            for (int i = 0; i < 7; ++i) {
+                IB_CUDA(cudaStreamCreateWithFlags(&aux[dev][i], cudaStreamNonBlocking));
+                IB_CUDA(cudaEventCreateWithFlags(&join_ev[dev][i], cudaEventDisableTiming));
+            }
+        }
+    }
+    if (nmat > 8) fail(IB_ERR_ARG, "ib_w_apply_many: at most 8 matrices per call");
+    IB_CUDA(cudaEventRecord(fork_ev[dev], s));
+    for (int i = 1; i < nmat; ++i) {
+        IB_CUDA(cudaStreamWaitEvent(aux[dev][i - 1], fork_ev[dev], 0));
+        apply_dev(*W[i]->w, dX, ldx, nvar, dY[i], ldy[i], force, aux[dev][i - 1]);
+        IB_CUDA(cudaEventRecord(join_ev[dev][i - 1], aux[dev][i - 1]));
+    }
+    apply_dev(*W[0]->w, dX, ldx, nvar, dY[0], ldy[0], force, s);
+    for (int i = 1; i < nmat; ++i) IB_CUDA(cudaStreamWaitEvent(s, join_ev[dev][i - 1], 0));
+}
+
+int ib_w_apply_many_dev(int32_t nmat, const ib_weighted *const *W, const double *dX, int64_t ldx, int32_t nvar, double *const *dY,
+                        const int64_t *ldy, int force_conservation, void *stream)
+{
+    IB_TRY
+    if (nmat <= 0 || !W || !dX || !dY || !ldy) fail(IB_ERR_ARG, "ib_w_apply_many_dev: bad argument");
+    for (int i = 0; i < nmat; ++i) {
+        if (!W[i] || !dY[i]) fail(IB_ERR_ARG, "ib_w_apply_many_dev: null matrix or output");
+        if (W[i]->w->ncol != W[0]->w->ncol) fail(IB_ERR_DIM, "ib_w_apply_many_dev: the matrices must share their input space");
+        for (int k = 0; k < i; ++k) if (W[k] == W[i]) fail(IB_ERR_ARG, "ib_w_apply_many_dev: the same matrix appears twice");
+    }
+    apply_many(nmat, W, dX, ldx, nvar, dY, ldy, force_conservation != 0, stream ? (cudaStream_t)stream : W[0]->w->stream);
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_w_apply_many(int32_t nmat, const ib_weighted *const *W, const double *X, int64_t ldx, int32_t nvar, double *const *Y,
+                    const int64_t *ldy, int layout, int force_conservation)
+{
+    IB_TRY
+    if (nmat <= 0 || nmat > 8 || !W || !X || !Y || !ldy || nvar <= 0) fail(IB_ERR_ARG, "ib_w_apply_many: bad argument");
+    for (int i = 0; i < nmat; ++i) {
+        if (!W[i] || !Y[i]) fail(IB_ERR_ARG, "ib_w_apply_many: null matrix or output");
+        if (W[i]->w->ncol != W[0]->w->ncol) fail(IB_ERR_DIM, "ib_w_apply_many: the matrices must share their input space");
+        for (int k = 0; k < i; ++k) if (W[k] == W[i]) fail(IB_ERR_ARG, "ib_w_apply_many: the same matrix appears twice");
+    }
+    cudaStream_t s = W[0]->w->stream;
+    const int64_t ncol = W[0]->w->ncol;
+    const int64_t ldd = (nvar + 1) & ~1;
+    DBuf<double> dX((size_t)ncol * ldd, s), tX;
+    std::vector<DBuf<double>> dY(nmat), tY(nmat);
+    std::vector<double *> dYp(nmat);
+    std::vector<int64_t> ldys(nmat, ldd);
+    for (int i = 0; i < nmat; ++i) { dY[i].alloc((size_t)W[i]->w->nrow * ldd, s); dYp[i] = dY[i].p; }
+    if (layout == IB_LAYOUT_CELL_MAJOR) {
+        if (ldx < nvar) fail(IB_ERR_ARG, "ib_w_apply_many: leading dimension smaller than nvar");
+        IB_CUDA(cudaMemcpy2DAsync(dX.p, ldd * 8, X, ldx * 8, (size_t)nvar * 8, (size_t)ncol, cudaMemcpyHostToDevice, s));
+    } else if (layout == IB_LAYOUT_FIELD_MAJOR) {
+        if (ldx < ncol) fail(IB_ERR_ARG, "ib_w_apply_many: leading dimension smaller than the cell count");
+        tX.alloc((size_t)nvar * ncol, s);
+        IB_CUDA(cudaMemcpy2DAsync(tX.p, ncol * 8, X, ldx * 8, (size_t)ncol * 8, (size_t)nvar, cudaMemcpyHostToDevice, s));
+        transpose(tX.p, ncol, nvar, ncol, dX.p, ldd, s);
+    } else {
+        fail(IB_ERR_ARG, "ib_w_apply_many: unknown layout %d", layout);
+    }
+    apply_many(nmat, W, dX.p, ldd, nvar, dYp.data(), ldys.data(), force_conservation != 0, s);
+    for (int i = 0; i < nmat; ++i) {
+        const int64_t nrow = W[i]->w->nrow;
+        if (layout == IB_LAYOUT_CELL_MAJOR) {
+            if (ldy[i] < nvar) fail(IB_ERR_ARG, "ib_w_apply_many: leading dimension smaller than nvar");
+            IB_CUDA(cudaMemcpy2DAsync(Y[i], ldy[i] * 8, dY[i].p, ldd * 8, (size_t)nvar * 8, (size_t)nrow, cudaMemcpyDeviceToHost, s));
+        } else {
+            if (ldy[i] < nrow) fail(IB_ERR_ARG, "ib_w_apply_many: leading dimension smaller than the cell count");
+            tY[i].alloc((size_t)nvar * nrow, s);
+            transpose(dY[i].p, ldd, nrow, nvar, tY[i].p, nrow, s);
+            IB_CUDA(cudaMemcpy2DAsync(Y[i], ldy[i] * 8, tY[i].p, nrow * 8, (size_t)nrow * 8, (size_t)nvar, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    IB_CUDA(cudaStreamSynchronize(s));
+    return IB_OK;
+    IB_CATCH
+}
+
 int ib_w_apply_rows_dev(const ib_weighted *W, const double *dX, int64_t ldx, int32_t nvar, double *dY, int64_t ldy, int64_t row_begin,
                         int64_t row_end, void *stream)
 {

@@ -125,6 +125,14 @@ int ib_w_apply(const ib_weighted *, const double *X, int64_t ldx, int32_t nvar, 
                int force_conservation);
 int ib_w_apply_dev(const ib_weighted *, const double *dX, int64_t ldx, int32_t nvar, double *dY, int64_t ldy,
                    int force_conservation, void *stream);          /* cell-major only */
+/* Several matrices applied to the SAME input fields in one call -- the coupler's pattern: EvI and AvI both act on
+ * ice_ovalsI (IceCoupler.cpp:445-446).  The applies are independent, so they run concurrently on internal streams
+ * (forked from / joined to `stream`), and the host version uploads X once.  dY[i] / Y[i]: output of W[i]. */
+int ib_w_apply_many_dev(int32_t nmat, const ib_weighted *const *W, const double *dX, int64_t ldx, int32_t nvar,
+                        double *const *dY, const int64_t *ldy, int force_conservation, void *stream);
+int ib_w_apply_many(int32_t nmat, const ib_weighted *const *W, const double *X, int64_t ldx, int32_t nvar, double *const *Y,
+                    const int64_t *ldy, int layout, int force_conservation);
+
 /* Row-block sharding of an apply across GPUs (north star: "output row blocks of the I/E grids are split across GPUs with
  * input fields replicated" -- no collective): computes only output rows [row_begin, row_end) of dY = M dX.
  * row_begin and row_end must be multiples of 32 (row_end may also be nrow).  No conservation correction. */

@@ -111,3 +111,19 @@ def test_row_block_sharding(cfg2, spec, nvar):
     from icebin_b200 import api
     with pytest.raises(api.IceBinError):
         M.apply_rows_dev(X.data_ptr(), nvar, nvar, Y.data_ptr(), nvar, 5, 64)
+
+
+def test_apply_many_matches_single_applies(cfg2):
+    """ib_w_apply_many: EvI and AvI on the same fields, concurrently; identical to the one-at-a-time results."""
+    from icebin_b200 import api
+    gg = make_gpu(cfg2)
+    rm = gg.regrid_matrices(cfg2["sheets"][0].name, cfg2["elevmask"][0], scale=True, correctA=True)
+    EvI, AvI = rm.matrix("EvI"), rm.matrix("AvI")
+    X = np.random.default_rng(0).uniform(-1, 1, (EvI.shape[1], 64))
+    for rep in range(3):
+        YE, YA = api.apply_many([EvI, AvI], X, layout="cell")
+        assert np.array_equal(YE, EvI.apply(X, layout="cell")) and np.array_equal(YA, AvI.apply(X, layout="cell"))
+    YEf, YAf = api.apply_many([EvI, AvI], np.ascontiguousarray(X.T), layout="field")
+    assert np.array_equal(YEf.T, YE) and np.array_equal(YAf.T, YA)
+    with pytest.raises(api.IceBinError):
+        api.apply_many([EvI, rm.matrix("IvE")], X, layout="cell")      # different input spaces
