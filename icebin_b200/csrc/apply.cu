@@ -34,6 +34,7 @@ namespace ib {
 
 constexpr int APPLY_CHUNK = 32;
 constexpr int GROUP_ROWS = 32;
+static int pair_chunk() { static int v = getenv("IB_PAIR_CHUNK") ? atoi(getenv("IB_PAIR_CHUNK")) : 32; return v; }
 
 // ---- plan -----------------------------------------------------------------------------------------------
 // item = (first_row, nnz_begin, nnz_end, w):  w >= 0: chunk of a long row, w = partial slot
@@ -81,6 +82,13 @@ struct PlanApply {
 };
 
 static bool make_pair_plan(Weighted &W, cudaStream_t s);
+struct MaxU32 {
+    __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+struct RowLenLoad {
+    const int32_t *rowptr;
+    __device__ uint32_t operator()(int64_t r) const { return (uint32_t)(rowptr[r + 1] - rowptr[r]); }
+};
 
 static void make_plan(Weighted &W, cudaStream_t s)
 {
@@ -99,6 +107,14 @@ static void make_plan(Weighted &W, cudaStream_t s)
         P.split_rows.alloc((size_t)P.nsplit_rows, s);
         P.slot_srow.alloc((size_t)P.npartials, s);
         scan_apply<uint4>(st, L, AddU32x4{}, z, PlanApply{L, W.nrow, P.items.p, P.split_rows.p, P.slot_srow.p}, s);
+        {
+            ScanState<uint32_t> ms;
+            transform_scan<uint32_t>(ms, W.nrow, RowLenLoad{W.rowptr.p}, MaxU32{}, 0u, s);
+            uint32_t mx = 0;
+            IB_CUDA(cudaMemcpyAsync(&mx, ms.total.p, sizeof mx, cudaMemcpyDeviceToHost, s));
+            IB_CUDA(cudaStreamSynchronize(s));
+            P.max_row_len = (int)mx;
+        }
         make_pair_plan(W, s);
     }
     P.ready = true;
@@ -152,14 +168,12 @@ struct VEmit {
 struct PairLoad {
     const uint64_t *key;
     const uint32_t *gstart;      // group start of every position
-    __device__ uint32_t operator()(int64_t p) const { return ((uint32_t)p - gstart[p]) % APPLY_CHUNK == 0 ? 1u : 0u; }
+    uint32_t chunk;
+    __device__ uint32_t operator()(int64_t p) const { return ((uint32_t)p - gstart[p]) % chunk == 0 ? 1u : 0u; }
 };
 struct GroupStartLoad {          // max-scan of (head ? p + 1 : 0)
     const uint64_t *key;
     __device__ uint32_t operator()(int64_t p) const { return (p == 0 || key[p] != key[p - 1]) ? (uint32_t)p + 1u : 0u; }
-};
-struct MaxU32 {
-    __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
 };
 struct GroupStartStore {
     const uint64_t *key;
@@ -173,6 +187,7 @@ struct PairEmit {
     const uint32_t *perm;
     const double *val;
     int64_t nv;
+    int chunk;
     int4 *items;
     int32_t *pcol;
     double *pv0, *pv1;
@@ -187,7 +202,7 @@ struct PairEmit {
         pv1[p] = ((int)q + 1 < colptr[c + 1]) ? val[perm[q + 1]] : 0.0;
         if (!start) return;
         int64_t e = p + 1;
-        while (e < nv && e - p < APPLY_CHUNK && key[e] == k) ++e;
+        while (e < nv && e - p < chunk && key[e] == k) ++e;
         const int32_t r0 = (int32_t)(k >> 32), r1 = (int32_t)(uint32_t)k - 1;
         items[prefix] = make_int4(r0, (int)p, (int)e, (int)(2 * prefix));
         fxkey[2 * prefix] = (uint32_t)r0; fxslot[2 * prefix] = 2 * prefix;
@@ -233,7 +248,7 @@ static bool make_pair_plan(Weighted &W, cudaStream_t s)
     ScanState<uint32_t> gs, is;
     transform_scan<uint32_t>(gs, nv, GroupStartLoad{key}, MaxU32{}, 0u, s);
     scan_apply<uint32_t>(gs, GroupStartLoad{key}, MaxU32{}, 0u, GroupStartStore{key, gstart.p}, s);
-    transform_scan<uint32_t>(is, nv, PairLoad{key, gstart.p}, AddU32{}, 0u, s);
+    transform_scan<uint32_t>(is, nv, PairLoad{key, gstart.p, (uint32_t)pair_chunk()}, AddU32{}, 0u, s);
     uint32_t nitems = 0;
     IB_CUDA(cudaMemcpyAsync(&nitems, is.total.p, sizeof nitems, cudaMemcpyDeviceToHost, s));
     IB_CUDA(cudaStreamSynchronize(s));
@@ -244,8 +259,8 @@ static bool make_pair_plan(Weighted &W, cudaStream_t s)
     P.pv0.alloc((size_t)nv, s);
     P.pv1.alloc((size_t)nv, s);
     DBuf<uint32_t> fk0(2 * (size_t)nitems, s), fk1(2 * (size_t)nitems, s), fs0(2 * (size_t)nitems, s), fs1(2 * (size_t)nitems, s);
-    scan_apply<uint32_t>(is, PairLoad{key, gstart.p}, AddU32{}, 0u,
-                         PairEmit{key, vid, vcol.p, vent.p, colptr.p, perm, W.val.p, nv, P.pair_items.p, P.pcol.p, P.pv0.p, P.pv1.p, fk0.p, fs0.p}, s);
+    scan_apply<uint32_t>(is, PairLoad{key, gstart.p, (uint32_t)pair_chunk()}, AddU32{}, 0u,
+                         PairEmit{key, vid, vcol.p, vent.p, colptr.p, perm, W.val.p, nv, pair_chunk(), P.pair_items.p, P.pcol.p, P.pv0.p, P.pv1.p, fk0.p, fs0.p}, s);
     // fix-up lists: (row, slot) sorted by row, slots ascending inside a row (stable)
     const int64_t nfx = 2 * (int64_t)nitems;
     const int w3 = radix_sort_pairs<uint32_t, uint32_t>(fk0.p, fs0.p, fk1.p, fs1.p, nfx, 32, s);
@@ -534,6 +549,101 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
     }
 }
 
+// ---- X-stationary kernel: tall matrices with few columns (IvE, IvA, smoothed IvE) ------------------------------
+// When the input space is small (E or A cells: ~10^3) and the output space large (ice cells: 10^5..10^7), a field slice
+// of ALL of X fits in shared memory: Xs[ncol][F] with F = 8..64 fields.  A CTA keeps one slice resident and streams
+// matrix rows through it: thread (row, p) walks its row's nonzeros, reads X from shared memory and writes one double2
+// of Y -- X costs no L2 traffic per nonzero (the row-streaming kernel re-fetches a 4 KB X row per nonzero, which is what
+// made IvE 0.42 and the 16-nnz/row smoothed IvE L2-bound).  The price is that the matrix is re-read once per slice.
+// Rows are never split: every row is summed over ascending columns with mul-then-add, i.e. bit-identical to the oracle.
+struct XsArgs {
+    const int32_t *rowptr, *col;
+    const double *val, *X;
+    int64_t ldx;
+    double *Y;
+    int64_t ldy;
+    int64_t nrow;
+    int ncol, nvar, F, nslice;
+    int64_t nchunk, nunits;
+    int chunk_rows;
+};
+
+constexpr int XS_THREADS = 1024;
+constexpr int XS_K = 4;          // rows in flight per thread (independent load chains)
+
+__global__ void __launch_bounds__(XS_THREADS) spmm_xs_kernel(const XsArgs a)
+{
+    extern __shared__ __align__(16) unsigned char xs_raw[];
+    double2 *Xs = reinterpret_cast<double2 *>(xs_raw);
+    const int TPR = a.F >> 1;                       // threads (double2) per row
+    const int rpp = blockDim.x / TPR;               // rows per pass
+    const int p = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+    // contiguous share of the (slice-major) unit list: a CTA changes slice at most a couple of times
+    const int64_t u0 = a.nunits * blockIdx.x / gridDim.x, u1 = a.nunits * (blockIdx.x + 1) / gridDim.x;
+    int cur_slice = -1;
+    for (int64_t u = u0; u < u1; ++u) {
+        const int slice = (int)(u / a.nchunk);
+        const int64_t chunk = u - (int64_t)slice * a.nchunk;
+        const int f0 = slice * a.F;
+        const int fw = min(a.F, a.nvar - f0) >> 1;  // live double2 per row in this slice
+        if (slice != cur_slice) {
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < a.ncol * TPR; idx += blockDim.x) {
+                const int c = idx / TPR, q = idx - c * TPR;
+                Xs[idx] = q < fw ? __ldg(reinterpret_cast<const double2 *>(a.X + (int64_t)c * a.ldx + f0) + q) : make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+            cur_slice = slice;
+        }
+        const int64_t r_end = min(a.nrow, (chunk + 1) * a.chunk_rows);
+        for (int64_t rb = chunk * a.chunk_rows + rl; rb < r_end; rb += (int64_t)rpp * XS_K) {
+            int jb[XS_K], je[XS_K];
+#pragma unroll
+            for (int k = 0; k < XS_K; ++k) {
+                const int64_t r = rb + (int64_t)k * rpp;
+                const bool ok = r < r_end;
+                jb[k] = ok ? __ldg(a.rowptr + r) : 0;
+                je[k] = ok ? __ldg(a.rowptr + r + 1) : 0;
+            }
+            // first two nonzeros of every row up front (IvE / IvA rows have 1..4): independent loads
+            int c0[XS_K], c1[XS_K];
+            double v0[XS_K], v1[XS_K];
+#pragma unroll
+            for (int k = 0; k < XS_K; ++k) {
+                const bool h0 = jb[k] < je[k], h1 = jb[k] + 1 < je[k];
+                c0[k] = h0 ? __ldg(a.col + jb[k]) : 0;
+                v0[k] = h0 ? __ldg(a.val + jb[k]) : 0.0;
+                c1[k] = h1 ? __ldg(a.col + jb[k] + 1) : 0;
+                v1[k] = h1 ? __ldg(a.val + jb[k] + 1) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < XS_K; ++k) {
+                const int64_t r = rb + (int64_t)k * rpp;
+                if (r >= r_end) continue;
+                double a0 = 0.0, a1 = 0.0;
+                if (jb[k] < je[k]) { const double2 x = Xs[c0[k] * TPR + p]; a0 = a0 + v0[k] * x.x; a1 = a1 + v0[k] * x.y; }
+                if (jb[k] + 1 < je[k]) { const double2 x = Xs[c1[k] * TPR + p]; a0 = a0 + v1[k] * x.x; a1 = a1 + v1[k] * x.y; }
+                int j = jb[k] + 2;
+                for (; j + 4 <= je[k]; j += 4) {
+                    int cc[4];
+                    double vv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { cc[q] = __ldg(a.col + j + q); vv[q] = __ldg(a.val + j + q); }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const double2 x = Xs[cc[q] * TPR + p]; a0 = a0 + vv[q] * x.x; a1 = a1 + vv[q] * x.y; }
+                }
+                for (; j < je[k]; ++j) {
+                    const int cq = __ldg(a.col + j);
+                    const double vq = __ldg(a.val + j);
+                    const double2 x = Xs[cq * TPR + p];
+                    a0 = a0 + vq * x.x; a1 = a1 + vq * x.y;
+                }
+                if (p < fw) reinterpret_cast<double2 *>(a.Y + r * a.ldy + f0)[p] = make_double2(a0, a1);
+            }
+        }
+    }
+}
+
 // ---- plain-load fallback (small / odd nvar, unaligned buffers) ---------------------------------------------
 // A group of L lanes (power of two) owns one (item, field-tile) unit; lane fl owns VEC consecutive fields.
 template <int VEC>
@@ -655,12 +765,49 @@ __global__ void wdot_final_kernel(const double *__restrict__ pa, int nba, const 
     for (int b = 0; b < nbb; ++b) tb = tb + pb[(int64_t)b * nvar + f];
     factor[f] = ta * (1. / tb);
 }
-__global__ void scale_fields_kernel(double *__restrict__ Y, int64_t ldy, int64_t nrow, int nvar, const double *__restrict__ factor)
+__global__ void scale_copy_kernel(const double *__restrict__ X, int64_t ldx, double *__restrict__ Xs, int64_t ldxs, int64_t nrow, int nvar,
+                                  const double *__restrict__ factor)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t r = t / nvar;
     int f = (int)(t - r * nvar);
-    if (r < nrow) Y[r * ldy + f] = Y[r * ldy + f] * factor[f];
+    if (r < nrow) Xs[r * ldxs + f] = X[r * ldx + f] * factor[f];
+}
+// v[c] = sum_r M[r,c] * wM[r], columns walked in CSC order (rows ascending): deterministic
+__global__ void cons_v_kernel(const int32_t *colptr, const uint32_t *perm, const int32_t *row, const double *val, const double *wM,
+                              int64_t ncol, double *v)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    double s = 0;
+    for (int32_t j = colptr[c]; j < colptr[c + 1]; ++j) { const uint32_t e = perm[j]; s += val[e] * wM[row[e]]; }
+    v[c] = s;
+}
+__global__ void expand_rows_kernel(const int32_t *rowptr, int64_t nrow, int32_t *row);
+__global__ void u32_to_i32_copy_kernel(const uint32_t *a, int64_t n, int32_t *b);
+
+static void compute_cons_v(Weighted &W, cudaStream_t s)
+{
+    if (W.cons_v.n == (size_t)W.ncol && W.ncol > 0) return;
+    const int64_t nnz = W.nnz, ncol = W.ncol, nrow = W.nrow;
+    W.cons_v.alloc((size_t)ncol, s);
+    W.cons_v.zero();
+    if (nnz == 0) return;
+    DBuf<int32_t> row((size_t)nnz, s), csorted((size_t)nnz, s), colptr((size_t)ncol + 1, s);
+    DBuf<uint32_t> k0((size_t)nnz, s), k1((size_t)nnz, s), p0((size_t)nnz, s), p1((size_t)nnz, s);
+    expand_rows_kernel<<<(unsigned)cdiv(nrow, 128), 128, 0, s>>>(W.rowptr.p, nrow, row.p);
+    IB_LAUNCHED();
+    IB_CUDA(cudaMemcpyAsync(k0.p, W.col.p, nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    iota_u32_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(p0.p, nnz);
+    IB_LAUNCHED();
+    const int w1 = radix_sort_pairs<uint32_t, uint32_t>(k0.p, p0.p, k1.p, p1.p, nnz, bits_for(ncol), s);
+    u32_to_i32_copy_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(w1 ? k1.p : k0.p, nnz, csorted.p);
+    IB_LAUNCHED();
+    colptr.zero();
+    seg_ptr_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(csorted.p, nnz, ncol, colptr.p);
+    IB_LAUNCHED();
+    cons_v_kernel<<<(unsigned)cdiv(ncol, 128), 128, 0, s>>>(colptr.p, w1 ? p1.p : p0.p, row.p, W.val.p, W.wM.p, ncol, W.cons_v.p);
+    IB_LAUNCHED();
 }
 
 static void wdot(const double *w, const double *A, int64_t lda, int64_t nrow, int nvar, DBuf<double> &part, int &nb, cudaStream_t s)
@@ -709,6 +856,27 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         if (row_begin == row_end) return;
     }
     const int rlo = (int)row_begin, rhi = (int)row_end;
+    // ---- conservation correction (ibmisc Weighted_Eigen::apply_e; matrix_formats.rst:156-165), fused as a prologue:
+    //   B = B0 * (Mw.A)/(wM.B0)  with  wM.(M A) = (M^T wM).A =: v.A ,
+    // so both dot products run over the (small) input fields, the factor is folded into a scaled copy of A, and the
+    // large output is written once instead of being re-read twice.
+    DBuf<double> Xscaled;
+    if (!W.conservative && force_conservation) {
+        compute_cons_v(W, s);
+        DBuf<double> pa, pb, factor((size_t)nvar, s);
+        int nba, nbb;
+        wdot(W.Mw.p, dX, ldx, W.ncol, nvar, pa, nba, s);
+        wdot(W.cons_v.p, dX, ldx, W.ncol, nvar, pb, nbb, s);
+        wdot_final_kernel<<<(unsigned)cdiv(nvar, 128), 128, 0, s>>>(pa.p, nba, pb.p, nbb, nvar, factor.p);
+        IB_LAUNCHED();
+        const int64_t ldxs = (nvar + 1) & ~1;
+        Xscaled.alloc((size_t)W.ncol * ldxs, s);
+        const int64_t tot = W.ncol * (int64_t)nvar;
+        scale_copy_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, s>>>(dX, ldx, Xscaled.p, ldxs, W.ncol, nvar, factor.p);
+        IB_LAUNCHED();
+        dX = Xscaled.p;
+        ldx = ldxs;
+    }
     if (ldx < nvar || ldy < nvar) fail(IB_ERR_ARG, "apply: leading dimension smaller than nvar");
     make_plan(W, s);
     ApplyPlan &P = W.plan;
@@ -719,7 +887,35 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
     static const int variant = getenv("IB_SPMM_VARIANT") ? atoi(getenv("IB_SPMM_VARIANT")) : 0;   // 0 auto, 1 LDG, 2 TMA
     static const int want_bps = getenv("IB_SPMM_BPS") ? atoi(getenv("IB_SPMM_BPS")) : 4;            // TMA blocks per SM
     bool done = false, pair_done = false;
-    if (vec2 && nvar >= 64 && variant != 1) {
+    static int max_smem_xs = 0;
+    if (!max_smem_xs) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_smem_xs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        IB_CUDA(cudaFuncSetAttribute(spmm_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_xs));
+    }
+    // X-stationary path: tall matrix, few columns, no long rows (variant 3 forces it, 4 forbids it)
+    if (vec2 && !ranged && variant != 1 && variant != 2 && variant != 4 && W.ncol > 0 && W.nrow >= 8 * W.ncol && P.max_row_len <= 256 && nvar >= 8 &&
+        (variant == 3 || 2 * W.nnz >= 3 * W.nrow)) {
+        int F = 64;
+        while (F > nvar) F >>= 1;
+        while (F >= 8 && (size_t)W.ncol * F * 8 > (size_t)max_smem_xs - 1024) F >>= 1;
+        if (F >= 8) {
+            const size_t smem = (size_t)W.ncol * F * 8;
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_xs_kernel, XS_THREADS, smem);
+            occ = std::max(1, std::min(occ, 4));
+            XsArgs a{W.rowptr.p, W.col.p, W.val.p, dX, ldx, dY, ldy, W.nrow, (int)W.ncol, nvar, F, (nvar + F - 1) / F, 0, 0, 2048};
+            a.nchunk = cdiv(W.nrow, a.chunk_rows);
+            a.nunits = a.nchunk * a.nslice;
+            const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(a.nunits, (int64_t)sm_count() * occ));
+            spmm_xs_kernel<<<(unsigned)nblk, XS_THREADS, smem, s>>>(a);
+            IB_LAUNCHED();
+            done = true;
+            pair_done = true;      // nothing to fix up
+        }
+    }
+    if (!done && vec2 && nvar >= 64 && variant != 1) {
         const int tw = std::min(nvar, TMA_MAX_TW);
         const int ntile = (nvar + tw - 1) / tw;
         const int64_t nunits = P.nitems * ntile;
@@ -800,17 +996,6 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
             int64_t tot = P.nsplit_rows * (int64_t)nvar;
             launch_dependent(spmm_fixup_kernel<1>, (unsigned)cdiv(tot, 256), 256, 0, s, P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy, rlo, rhi);
         }
-    }
-    if (!W.conservative && force_conservation) {
-        DBuf<double> pa, pb, factor((size_t)nvar, s);
-        int nba, nbb;
-        wdot(W.Mw.p, dX, ldx, W.ncol, nvar, pa, nba, s);
-        wdot(W.wM.p, dY, ldy, W.nrow, nvar, pb, nbb, s);
-        wdot_final_kernel<<<(unsigned)cdiv(nvar, 128), 128, 0, s>>>(pa.p, nba, pb.p, nbb, nvar, factor.p);
-        IB_LAUNCHED();
-        int64_t tot = W.nrow * (int64_t)nvar;
-        scale_fields_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, s>>>(dY, ldy, W.nrow, nvar, factor.p);
-        IB_LAUNCHED();
     }
 }
 

@@ -81,6 +81,7 @@ struct ApplyPlan {
     DBuf<int4> split_rows;   // (row, first_partial, nchunks, 0)
     int64_t npartials = 0;
     DBuf<int32_t> slot_srow; // partial slot -> split-row index
+    int max_row_len = 0;     // longest row (X-stationary kernel eligibility)
     // pair-grouped column plan (matrices with <= 2 nonzeros per column, e.g. EvI): columns sharing the same pair
     // of rows are chunked together so that each X row is read once and feeds both output rows
     bool pair = false;
