@@ -277,40 +277,67 @@ struct HeadLoad {
 };
 struct ReduceApply {
     const uint64_t *keys;
-    const double *vals;
-    int64_t n;
     int cbits;
-    int32_t *row, *col;
-    double *val;
+    int32_t *row, *col, *segstart;
     __device__ void operator()(int64_t i, uint32_t prefix, uint32_t head) const
     {
         if (!head) return;
         const uint64_t k = keys[i];
-        double v = vals[i];
-        for (int64_t t = i + 1; t < n && keys[t] == k; ++t) v += vals[t];
         row[prefix] = (int32_t)(k >> cbits);
         col[prefix] = (int32_t)(k & ((uint64_t(1) << cbits) - 1));
-        val[prefix] = v;
+        segstart[prefix] = (int32_t)i;
     }
 };
 
-// sequential (reference-order) sums: rows in CSR order, columns through the CSC permutation
-__global__ void row_sum_kernel(const int32_t *rowptr, const double *val, int64_t nrow, double *out)
+// Segmented sums out[g] = sum_{j in [ptr[g], ptr[g+1])} val[perm ? perm[j] : j].
+// Segments of <= SEG_SEQ elements are summed sequentially by one thread, in storage order -- the order in which Eigen
+// sums duplicate triplets and ibmisc's sum() walks a matrix, so those results are bit-identical to the oracle.
+// Longer segments (EvA/AvE: thousands of exchange cells per (E, A) pair; A-grid weights at 1 km) would serialise one
+// thread for milliseconds; they are queued and reduced by one warp each: lane-strided partial sums followed by a
+// fixed butterfly, i.e. deterministic, differing from the sequential order only in association (<= 1e-13 relative).
+constexpr int SEG_SEQ = 64;
+__global__ void seg_sum_short_kernel(const int32_t *__restrict__ ptr, const uint32_t *__restrict__ perm, const double *__restrict__ val,
+                                     int64_t nseg, double *__restrict__ out, int32_t *__restrict__ long_list, int *__restrict__ nlong)
 {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrow) return;
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nseg) return;
+    const int32_t b = ptr[g], e = ptr[g + 1];
+    if (e - b > SEG_SEQ) { long_list[atomicAdd(nlong, 1)] = (int32_t)g; return; }
     double s = 0;
-    for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) s += val[j];
-    out[r] = s;
+    if (perm) for (int32_t j = b; j < e; ++j) s += val[perm[j]];
+    else for (int32_t j = b; j < e; ++j) s += val[j];
+    out[g] = s;
 }
-__global__ void col_sum_kernel(const int32_t *colptr, const uint32_t *perm, const double *val, int64_t ncol, double *out)
+__global__ void __launch_bounds__(256) seg_sum_long_kernel(const int32_t *__restrict__ ptr, const uint32_t *__restrict__ perm,
+                                                           const double *__restrict__ val, double *__restrict__ out,
+                                                           const int32_t *__restrict__ long_list, const int *__restrict__ nlong)
 {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncol) return;
-    double s = 0;
-    for (int32_t j = colptr[c]; j < colptr[c + 1]; ++j) s += val[perm[j]];
-    out[c] = s;
+    const int lane = threadIdx.x & 31;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const int n = *nlong;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nw) {
+        const int32_t g = long_list[w];
+        const int32_t b = ptr[g], e = ptr[g + 1];
+        double s = 0;
+        if (perm) for (int32_t j = b + lane; j < e; j += 32) s += val[perm[j]];
+        else for (int32_t j = b + lane; j < e; j += 32) s += val[j];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) out[g] = s;
+    }
 }
+static void seg_sum(const int32_t *ptr, const uint32_t *perm, const double *val, int64_t nseg, double *out, cudaStream_t s)
+{
+    if (nseg <= 0) return;
+    DBuf<int32_t> long_list((size_t)nseg, s);
+    DBuf<int> nlong(1, s);
+    nlong.zero();
+    seg_sum_short_kernel<<<(unsigned)cdiv(nseg, 128), 128, 0, s>>>(ptr, perm, val, nseg, out, long_list.p, nlong.p);
+    IB_LAUNCHED();
+    seg_sum_long_kernel<<<(unsigned)(2 * sm_count()), 256, 0, s>>>(ptr, perm, val, out, long_list.p, nlong.p);
+    IB_LAUNCHED();
+}
+
 __global__ void gather_i32_kernel(const uint32_t *perm, const int32_t *src, int64_t n, int32_t *dst)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -496,15 +523,19 @@ std::unique_ptr<Weighted> build_matrix(RegridMatrices &rm, std::string const &sp
     DBuf<int32_t> row((size_t)nnz, s);
     DBuf<double> rowsum((size_t)nrow, s), colsum((size_t)ncol, s), rowf((size_t)nrow, s);
     if (nnz > 0) {
-        scan_apply<uint32_t>(hs, HeadLoad<uint64_t>{sk}, AddU32{}, 0u,
-                             ReduceApply{sk, sv, ntrip, c.cbits, row.p, W->col.p, W->val.p}, s);
+        DBuf<int32_t> segstart((size_t)nnz + 1, s);
+        scan_apply<uint32_t>(hs, HeadLoad<uint64_t>{sk}, AddU32{}, 0u, ReduceApply{sk, c.cbits, row.p, W->col.p, segstart.p}, s);
+        const int32_t ntrip32 = (int32_t)ntrip;
+        IB_CUDA(cudaMemcpyAsync(segstart.p + nnz, &ntrip32, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        IB_CUDA(cudaStreamSynchronize(s));
+        seg_sum(segstart.p, nullptr, sv, nnz, W->val.p, s);      // duplicate (row, col) triplets summed in emission order
         seg_ptr_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(row.p, nnz, nrow, W->rowptr.p);
         IB_LAUNCHED();
     }
     k0.release(); k1.release(); v0.release(); v1.release();
 
     // ---- weights: row sums in CSR order, column sums in CSC order (the oracle's traversal orders)
-    if (nrow) { row_sum_kernel<<<(unsigned)cdiv(nrow, 128), 128, 0, s>>>(W->rowptr.p, W->val.p, nrow, rowsum.p); IB_LAUNCHED(); }
+    seg_sum(W->rowptr.p, nullptr, W->val.p, nrow, rowsum.p, s);
     {
         DBuf<uint32_t> ck0((size_t)nnz, s), ck1((size_t)nnz, s), pm0((size_t)nnz, s), pm1((size_t)nnz, s);
         DBuf<int32_t> colptr((size_t)ncol + 1, s), csorted((size_t)nnz, s);
@@ -521,7 +552,7 @@ std::unique_ptr<Weighted> build_matrix(RegridMatrices &rm, std::string const &sp
             seg_ptr_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(csorted.p, nnz, ncol, colptr.p);
             IB_LAUNCHED();
         }
-        if (ncol) { col_sum_kernel<<<(unsigned)cdiv(ncol, 128), 128, 0, s>>>(colptr.p, perm, W->val.p, ncol, colsum.p); IB_LAUNCHED(); }
+        seg_sum(colptr.p, perm, W->val.p, ncol, colsum.p, s);
     }
 
     // ---- diagonal ratios + scaling
