@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--nvar", type=int, default=512)
     ap.add_argument("--shape", default="greenland_5km")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="kernel experiments only; the driver never passes this")
     return ap.parse_args()
 
@@ -226,24 +227,76 @@ def run_b200(args):
         rm_u = gcm.regrid_matrices(sh.name, em_host, scale=False, correctA=True)
         EvI, AvI = rm_u.matrix("EvI"), rm_u.matrix("AvI")
         assert (EvI.shape, AvI.shape) == ((nE_d, nI_d), (nA_d, nI_d))
-        mergeA = multi.SheetMerge([(gcm.nE, EvI), (gcm.nA, AvI)], nvar, dev)
+        # two merge contexts + two sets of result buffers: the exchange of step s runs on a side stream while the
+        # SpMMs of step s+1 run on the main one (batches of fields are independent)
+        merges = [multi.SheetMerge([(gcm.nE, EvI), (gcm.nA, AvI)], nvar, dev) for _ in range(2)]
+        mergeA = merges[0]
+        side = torch.cuda.Stream(device=dev)
+        YEs = [YE, torch.empty_like(YE)]
+        YAs = [YA, torch.empty_like(YA)]
+        spmm_done = [torch.cuda.Event() for _ in range(2)]
+        merge_done = [torch.cuda.Event() for _ in range(2)]
 
     YE_p, YA_p = YE.data_ptr(), YA.data_ptr()
+    step_no = [0]
+    fresh = [True, True]       # no exchange pending on buffer set k (start of the run / of a captured graph)
 
     def step():
         # EvI and AvI act on the same ice-grid fields (IceCoupler.cpp:445-446): one batched call, the two independent
         # SpMMs run concurrently on forked streams and join back on `stream`
-        api.apply_many_dev([EvI, AvI], X.data_ptr(), nvar, nvar, [YE_p, YA_p], [nvar, nvar], True, stream)
+        if mergeA is None:
+            api.apply_many_dev([EvI, AvI], X.data_ptr(), nvar, nvar, [YE_p, YA_p], [nvar, nvar], True, stream)
+            return
+        k = step_no[0] & 1
+        step_no[0] += 1
+        if not fresh[k]:
+            tstream.wait_event(merge_done[k])             # buffers k are free again
+        fresh[k] = False
+        api.apply_many_dev([EvI, AvI], X.data_ptr(), nvar, nvar, [YEs[k].data_ptr(), YAs[k].data_ptr()], [nvar, nvar], True, stream)
+        spmm_done[k].record(tstream)
+        with torch.cuda.stream(side):
+            side.wait_event(spmm_done[k])
+            merges[k].run([YEs[k], YAs[k]], side.cuda_stream)
+            merge_done[k].record(side)
+
+    def drain():
         if mergeA is not None:
-            mergeA.begin(0, YE, stream)
-            mergeA.begin(1, YA, stream)
-            mergeA.finish([YE, YA], stream)
+            for k, e in enumerate(merge_done):
+                if not fresh[k]:
+                    tstream.wait_event(e)
+                fresh[k] = True
+            step_no[0] = 0
 
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     torch.cuda.synchronize()
+
+    # CUDA graph of GSTEPS consecutive steps (launch-bound otherwise: ~10 launches + a collective per 110 us step).
+    # The library's forked streams, its stream-ordered allocations and the NCCL all-reduce are all capturable.
+    GSTEPS = 8
+    graph, launches_per_graph = None, None
+    # single-GPU only: with NCCL inside the capture one rank falling back to eager while another replays would
+    # desynchronise the collectives, and the few percent it buys at N>1 are not worth that risk
+    if not args.no_graph and args.steps >= GSTEPS and world == 1:
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = api.launch_count()
+            with torch.cuda.graph(graph, stream=tstream):
+                for _ in range(GSTEPS):
+                    step()
+                drain()
+            launches_per_graph = api.launch_count() - l0
+            for _ in range(2):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:      # capture not supported in this setup: fall back to eager issue
+            sys.stderr.write("bench.py: CUDA graph capture failed (%s); running eagerly\n" % str(e).splitlines()[0])
+            graph = None
+            torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
@@ -252,12 +305,22 @@ def run_b200(args):
     l0 = api.launch_count()
     sampler.active = True
     ev[0].record()
-    for i in range(args.steps):
-        step()
+    if graph is not None:
+        nrep, rest = divmod(args.steps, GSTEPS)
+        for i in range(nrep):
+            graph.replay()
+        for i in range(rest):
+            step()
+    else:
+        for i in range(args.steps):
+            step()
+    drain()                     # the last exchanges are inside the timed region
     ev[1].record()
     torch.cuda.synchronize()
     sampler.active = False
     launches = api.launch_count() - l0
+    if graph is not None:
+        launches += (args.steps // GSTEPS) * launches_per_graph      # kernels replayed from the graph
     if world > 1:
         dist.barrier()
     ms = ev[0].elapsed_time(ev[1])
@@ -317,7 +380,7 @@ def run_b200(args):
     achieved = alg / (evi_ms * 1e-3) / 1e9
     if mergeA is not None:
         line_extra = {"merge": {"shared_E_cells": int(mergeA.parts[0]["nshared"]), "shared_A_cells": int(mergeA.parts[1]["nshared"]),
-                                "collective": "NCCL all-reduce(sum) of the shared rows' unscaled sums, %d B per step" %
+                                "collective": "NCCL all-reduce(sum) of the shared rows' unscaled sums on a side stream, overlapping the next step's SpMMs, %d B per step" %
                                               (mergeA.nshared * nvar * 8)}}
     else:
         line_extra = {}
@@ -333,7 +396,8 @@ def run_b200(args):
                          "timing": "EvI apply alone, CUDA events around each of `steps` applies issued right after the timed region",
                          "traffic": NCU_TRAFFIC_EVI if (args.shape == "greenland_5km" and nvar == 512) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of spmm_tma_kernel<1>, profiles/r1_spmm_tma_full_raw.csv"},
-            "gpu_launches": int(launches), "clocks": sampler.result()}
+            "gpu_launches": int(launches), "issue": ("CUDA graph of %d steps" % GSTEPS) if graph is not None else "eager",
+            "clocks": sampler.result()}
     line.update(line_extra)
     if e2e is not None:
         line["e2e"] = e2e

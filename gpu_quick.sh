@@ -1,3 +1,2 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -5 > gpurun_out/t.log
-python tools/build_one.py greenland_1km >> gpurun_out/t.log 2>&1
-python tools/build_one.py antarctica_1km >> gpurun_out/t.log 2>&1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 4 --steps 304 --warmup 10 > gpurun_out/bench_n4.log 2>&1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 304 --warmup 10 > gpurun_out/bench_n2.log 2>&1
