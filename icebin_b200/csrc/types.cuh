@@ -115,6 +115,5 @@ void smooth_rows(RegridMatrices &rm, Weighted &W, Params const &p);
 // apply.cu
 void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY, int64_t ldy, bool force_conservation,
                cudaStream_t s, int64_t row_begin = 0, int64_t row_end = -1);
-void csr_transpose_matvec(Weighted &W, const double *x_rows, double *y_cols, cudaStream_t s);
 
 }   // namespace ib

@@ -51,10 +51,8 @@ def test_greenland_1km_properties(gr1km):
         wM = torch.from_numpy(M.get_weights(0)).to(dev); Mw = torch.from_numpy(M.get_weights(1)).to(dev)
         lhs, rhs = (Y * wM[:, None]).sum(0), (X * Mw[:, None]).sum(0)
         assert torch.all(torch.abs(lhs / rhs - 1) < 1e-12), s
-        back = S["IvA" if s == "AvI" else "IvE"]
-        Z = torch.empty((nI, nvar), dtype=torch.float64, device=dev)
-        # correctA puts the native/proj ratio on the A/E side only, so E->I of (I->E of 1) is the ratio-weighted 1;
-        # the plain round trip is checked without correctA below
+    # correctA puts the native/proj ratio on the A/E side only, so E->I of (I->E of 1) is the ratio-weighted 1;
+    # the plain round trip is checked without correctA
     P = {s: g.regrid_matrices(sh.name, em, scale=True, correctA=False).matrix(s) for s in ("EvI", "IvE")}
     one = torch.ones((nI, 1), dtype=torch.float64, device=dev)
     yE = torch.empty((P["EvI"].shape[0], 1), dtype=torch.float64, device=dev)
