@@ -238,6 +238,16 @@ def run_b200(args):
         merge_done = [torch.cuda.Event() for _ in range(2)]
 
     YE_p, YA_p = YE.data_ptr(), YA.data_ptr()
+    # pre-built argument arrays for the C ABI (the per-step Python cost matters at a 110 us step)
+    import ctypes as C
+    from icebin_b200._lib import vp as _vp
+    _W2 = (_vp * 2)(EvI._h, AvI._h)
+    _ld2 = (C.c_int64 * 2)(nvar, nvar)
+    _Yp = [(_vp * 2)(YE_p, YA_p)]
+    if mergeA is not None:
+        _Yp = [(_vp * 2)(YEs[k].data_ptr(), YAs[k].data_ptr()) for k in range(2)]
+    _apply_many = lib().ib_w_apply_many_dev
+    _X, _st = _vp(X.data_ptr()), _vp(stream)
     step_no = [0]
     fresh = [True, True]       # no exchange pending on buffer set k (start of the run / of a captured graph)
 
@@ -245,14 +255,14 @@ def run_b200(args):
         # EvI and AvI act on the same ice-grid fields (IceCoupler.cpp:445-446): one batched call, the two independent
         # SpMMs run concurrently on forked streams and join back on `stream`
         if mergeA is None:
-            api.apply_many_dev([EvI, AvI], X.data_ptr(), nvar, nvar, [YE_p, YA_p], [nvar, nvar], True, stream)
+            check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[0], _ld2, 1, _st))
             return
         k = step_no[0] & 1
         step_no[0] += 1
         if not fresh[k]:
             tstream.wait_event(merge_done[k])             # buffers k are free again
         fresh[k] = False
-        api.apply_many_dev([EvI, AvI], X.data_ptr(), nvar, nvar, [YEs[k].data_ptr(), YAs[k].data_ptr()], [nvar, nvar], True, stream)
+        check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[k], _ld2, 1, _st))
         spmm_done[k].record(tstream)
         with torch.cuda.stream(side):
             side.wait_event(spmm_done[k])

@@ -81,6 +81,12 @@ class SheetMerge:
                     dist.all_reduce(part["wtot"], group=group)
             self.parts.append(part)
         self.nshared = sum(p["nshared"] for p in self.parts)
+        # one contiguous exchange buffer for all parts: run() then needs a single all-reduce
+        self.buf_all = torch.zeros((max(self.nshared, 1), nvar), dtype=torch.float64, device=device)
+        off = 0
+        for p in self.parts:
+            p["buf"] = self.buf_all[off: off + max(p["nshared"], 0)] if p["nshared"] else p["buf"]
+            off += p["nshared"]
 
     def begin(self, i, Y, stream):
         p, nvar = self.parts[i], self.nvar
@@ -100,6 +106,13 @@ class SheetMerge:
                                                       p["wtot"].data_ptr(), p["wlocal"].data_ptr(), stream))
 
     def run(self, Ys, stream):
-        for i, Y in enumerate(Ys):
-            self.begin(i, Y, stream)
-        self.finish(Ys, stream)
+        """pack every part, ONE all-reduce of the shared rows of all parts, unpack."""
+        L, nvar = self._lib, self.nvar
+        for p, Y in zip(self.parts, Ys):
+            if p["nshared"]:
+                self._check(L.ib_merge_pack_dev(Y.data_ptr(), nvar, nvar, p["loc"].data_ptr(), p["nshared"], p["buf"].data_ptr(), stream))
+        if self.nshared and self._multi:
+            dist.all_reduce(self.buf_all, group=self.group)
+        for p, Y in zip(self.parts, Ys):
+            self._check(L.ib_merge_unpack_dev(Y.data_ptr(), nvar, nvar, p["nrow"], p["slot"].data_ptr(), p["buf"].data_ptr(),
+                                              p["wtot"].data_ptr(), p["wlocal"].data_ptr(), stream))
