@@ -127,8 +127,11 @@ __global__ void __launch_bounds__(128) smooth_rows_kernel(const SmoothArgs a)
     int nslots = 0;
     double factor = 0.0;
 
-    // sweep 0: normaliser.  sweep 1: fold the neighbours' M rows.
-    for (int sweep = 0; sweep < 2; ++sweep) {
+    // sweep 0: normaliser (fill pass only).  sweep 1: fold the neighbours' M rows.
+    // In sweep 1 every lane first fetches ITS candidate's leading two matrix entries (lane-parallel, latencies overlap);
+    // the serial fold then only shuffles registers -- no dependent global load sits in the serial chain unless a
+    // neighbour's row has more than two entries.
+    for (int sweep = FILL ? 0 : 1; sweep < 2; ++sweep) {
         double denom = 0.0;
         for (int yy = by0; yy <= by1; ++yy)
         for (int xx = bx0; xx <= bx1; ++xx) {
@@ -144,35 +147,74 @@ __global__ void __launch_bounds__(128) smooth_rows_kernel(const SmoothArgs a)
                     const double dx = (a.t.x[tj] - x0) / a.sx, dy = (a.t.y[tj] - y0) / a.sy, dz = (a.t.z[tj] - z0) / a.sz;
                     double nd2 = 0.0;
                     nd2 += dx * dx; nd2 += dy * dy; nd2 += dz * dz;
-                    if (nd2 < 4.0) { acc = true; w = exp(-.5 * nd2) * a.t.area[tj]; }
+                    if (nd2 < 4.0) { acc = true; if (FILL) w = exp(-.5 * nd2) * a.t.area[tj]; }
                 }
                 if (sweep == 0) {
                     denom += w;       // lane-private partial; combined below in a fixed butterfly order
                     continue;
                 }
-                unsigned m = __ballot_sync(0xffffffffu, acc);
-                while (m) {
-                    const int src = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int dj = a.t.d[__shfl_sync(0xffffffffu, tj, src)];
-                    const double sij = factor * shfl_d(w, src);          // smoothI(i,j) = factor * (gauss * area)
-                    const int rb = __ldg(a.rowptr + dj), re = __ldg(a.rowptr + dj + 1);
-                    for (int e = rb; e < re; ++e) {
-                        const int c = __ldg(a.col + e);
-                        const double v = sij * __ldg(a.val + e);
-                        bool hit = false;
+                int rb = 0, nent = 0, c0 = -1, c1 = -1;
+                double v0 = 0.0, v1 = 0.0;
+                if (acc) {
+                    const int dj = a.t.d[tj];
+                    rb = __ldg(a.rowptr + dj);
+                    nent = __ldg(a.rowptr + dj + 1) - rb;
+                    const double sij = factor * w;                        // smoothI(i,j) = factor * (gauss * area)
+                    if (nent > 0) { c0 = __ldg(a.col + rb); if (FILL) v0 = sij * __ldg(a.val + rb); }
+                    if (nent > 1) { c1 = __ldg(a.col + rb + 1); if (FILL) v1 = sij * __ldg(a.val + rb + 1); }
+                    w = sij;
+                }
+                // fold one entry of a column slot table; `c`, `v` are warp-uniform
+                auto fold = [&](int c, double v) {
+                    bool hit = false;
 #pragma unroll
-                        for (int s = 0; s < SM_SPL; ++s)
-                            if (scol[s] == c) { sacc[s] += v; hit = true; }
-                        if (!__ballot_sync(0xffffffffu, hit)) {
-                            if (nslots < SM_CAP && lane == (nslots & 31)) {
+                    for (int s = 0; s < SM_SPL; ++s)
+                        if (scol[s] == c) { if (FILL) sacc[s] += v; hit = true; }
+                    if (!__ballot_sync(0xffffffffu, hit)) {
+                        if (nslots < SM_CAP && lane == (nslots & 31)) {
 #pragma unroll
-                                for (int s = 0; s < SM_SPL; ++s)
-                                    if (s == (nslots >> 5)) { scol[s] = c; sacc[s] = v; }
-                            }
-                            ++nslots;
+                            for (int s = 0; s < SM_SPL; ++s)
+                                if (s == (nslots >> 5)) { scol[s] = c; sacc[s] = v; }
+                        }
+                        ++nslots;
+                    }
+                };
+                // entries 0 and 1 of the batch: lanes whose neighbours feed the SAME column are combined first (their
+                // values added in lane order), so the slot search runs once per distinct column of the batch instead of
+                // once per neighbour -- neighbouring ice cells share their elevation classes
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int key = e == 0 ? c0 : c1;
+                    const double val = e == 0 ? v0 : v1;
+                    const unsigned mvalid = __ballot_sync(0xffffffffu, key >= 0);
+                    if (!mvalid) continue;
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    double gsum = 0.0;
+                    if (FILL) {
+                        unsigned mm = mvalid;
+                        while (mm) {
+                            const int k = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const double vk = shfl_d(val, k);
+                            if ((peers >> k) & 1u) gsum += vk;
                         }
                     }
+                    unsigned leaders = __ballot_sync(0xffffffffu, key >= 0 && lane == __ffs(peers) - 1);
+                    while (leaders) {
+                        const int src = __ffs(leaders) - 1;
+                        leaders &= leaders - 1;
+                        fold(__shfl_sync(0xffffffffu, key, src), FILL ? shfl_d(gsum, src) : 0.0);
+                    }
+                }
+                // neighbours whose M row has more than two entries: the rest, one neighbour at a time
+                unsigned mlong = __ballot_sync(0xffffffffu, acc && nent > 2);
+                while (mlong) {
+                    const int src = __ffs(mlong) - 1;
+                    mlong &= mlong - 1;
+                    const int ne = __shfl_sync(0xffffffffu, nent, src);
+                    const int pos0 = __shfl_sync(0xffffffffu, rb, src);
+                    const double sw = FILL ? shfl_d(w, src) : 0.0;
+                    for (int e = 2; e < ne; ++e) fold(__ldg(a.col + pos0 + e), FILL ? sw * __ldg(a.val + pos0 + e) : 0.0);
                 }
             }
         }
