@@ -127,12 +127,14 @@ __global__ void __launch_bounds__(128) smooth_rows_kernel(const SmoothArgs a)
     int nslots = 0;
     double factor = 0.0;
 
-    // sweep 0: normaliser (fill pass only).  sweep 1: fold the neighbours' M rows.
-    // In sweep 1 every lane first fetches ITS candidate's leading two matrix entries (lane-parallel, latencies overlap);
-    // the serial fold then only shuffles registers -- no dependent global load sits in the serial chain unless a
-    // neighbour's row has more than two entries.
-    for (int sweep = FILL ? 0 : 1; sweep < 2; ++sweep) {
-        double denom = 0.0;
+    // ONE sweep over the candidates: the normaliser sum_j(gauss_ij * area_j) and the un-normalised folds
+    // sum_j (gauss_ij * area_j) * M[j, c] are accumulated together and the row is scaled by 1/normaliser at the end
+    // (upstream scales every smoothI entry first, smoother.cpp:62-65: same value up to rounding).
+    // Every lane first fetches ITS candidate's leading two matrix entries (lane-parallel, latencies overlap); the
+    // serial part then only shuffles registers -- no dependent global load unless a neighbour's row has > 2 entries.
+    double denom = 0.0;
+    {
+        const int sweep = 1;
         for (int yy = by0; yy <= by1; ++yy)
         for (int xx = bx0; xx <= bx1; ++xx) {
             const int b = yy * a.g.nbx + xx;
@@ -149,17 +151,14 @@ __global__ void __launch_bounds__(128) smooth_rows_kernel(const SmoothArgs a)
                     nd2 += dx * dx; nd2 += dy * dy; nd2 += dz * dz;
                     if (nd2 < 4.0) { acc = true; if (FILL) w = exp(-.5 * nd2) * a.t.area[tj]; }
                 }
-                if (sweep == 0) {
-                    denom += w;       // lane-private partial; combined below in a fixed butterfly order
-                    continue;
-                }
+                denom += w;           // lane-private partial; combined below in a fixed butterfly order
                 int rb = 0, nent = 0, c0 = -1, c1 = -1;
                 double v0 = 0.0, v1 = 0.0;
                 if (acc) {
                     const int dj = a.t.d[tj];
                     rb = __ldg(a.rowptr + dj);
                     nent = __ldg(a.rowptr + dj + 1) - rb;
-                    const double sij = factor * w;                        // smoothI(i,j) = factor * (gauss * area)
+                    const double sij = w;                                 // gauss * area; 1/normaliser applied at the end
                     if (nent > 0) { c0 = __ldg(a.col + rb); if (FILL) v0 = sij * __ldg(a.val + rb); }
                     if (nent > 1) { c1 = __ldg(a.col + rb + 1); if (FILL) v1 = sij * __ldg(a.val + rb + 1); }
                     w = sij;
@@ -218,11 +217,14 @@ __global__ void __launch_bounds__(128) smooth_rows_kernel(const SmoothArgs a)
                 }
             }
         }
-        if (sweep == 0) {
+        (void)sweep;
+    }
+    if (FILL) {
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) denom += shfl_d(denom, lane ^ d);
-            factor = 1. / denom;
-        }
+        for (int d = 16; d > 0; d >>= 1) denom += shfl_d(denom, lane ^ d);
+        factor = 1. / denom;
+#pragma unroll
+        for (int s = 0; s < SM_SPL; ++s) sacc[s] = factor * sacc[s];
     }
     if (nslots > SM_CAP) {
         if (lane == 0) atomicMax(a.err + 3, nslots);
