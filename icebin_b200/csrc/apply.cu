@@ -25,6 +25,7 @@
 
 #include <cstdlib>
 
+#include "gc_plan.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "types.cuh"
@@ -82,6 +83,7 @@ struct PlanApply {
 };
 
 static bool make_pair_plan(Weighted &W, cudaStream_t s);
+static void make_gc_plan(Weighted &W, cudaStream_t s);
 struct MaxU32 {
     __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
 };
@@ -116,8 +118,54 @@ static void make_plan(Weighted &W, cudaStream_t s)
             P.max_row_len = (int)mx;
         }
         make_pair_plan(W, s);
+        if (P.max_row_len <= GC_S && P.nsplit_rows == 0 && !getenv("IB_SPMM_NOGC")) make_gc_plan(W, s);
     }
     P.ready = true;
+}
+
+// ---- distinct-column groups (gc_plan.cuh): one thread per 32-row block runs the greedy grouping twice
+// (count -> scan -> emit), exactly like the other plans
+struct GcCountLoad {
+    const int32_t *rowptr, *col;
+    int64_t nrow;
+    __device__ uint4 operator()(int64_t b) const
+    {
+        const GcCount c = gc_block<false>(rowptr, col, nullptr, nrow, b, 0u, 0u, nullptr, nullptr, nullptr);
+        return make_uint4(c.items, c.recs, 0u, 0u);
+    }
+};
+struct GcEmit {
+    const int32_t *rowptr, *col;
+    const double *val;
+    int64_t nrow;
+    GcItem *items;
+    int32_t *ucol;
+    GcRec *recs;
+    __device__ void operator()(int64_t b, uint4 prefix, uint4) const { gc_block<true>(rowptr, col, val, nrow, b, prefix.x, prefix.y, items, ucol, recs); }
+};
+static_assert(sizeof(GcItem) == sizeof(int4) && sizeof(GcRec) == sizeof(int4), "GcItem / GcRec must alias int4");
+
+static void make_gc_plan(Weighted &W, cudaStream_t s)
+{
+    ApplyPlan &P = W.plan;
+    const int64_t nblk = cdiv(W.nrow, GC_BLOCK);
+    ScanState<uint4> st;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    GcCountLoad L{W.rowptr.p, W.col.p, W.nrow};
+    transform_scan<uint4>(st, nblk, L, AddU32x4{}, z, s);
+    uint4 tot;
+    IB_CUDA(cudaMemcpyAsync(&tot, st.total.p, sizeof tot, cudaMemcpyDeviceToHost, s));
+    IB_CUDA(cudaStreamSynchronize(s));
+    P.gc_nitems = tot.x;
+    P.gc_items.alloc((size_t)tot.x, s);
+    P.gc_ucol.alloc((size_t)tot.x * GC_S, s);
+    P.gc_recs.alloc((size_t)tot.y + 2, s);         // the kernel's record prefetch runs two entries ahead
+    P.gc_recs.zero();
+    scan_apply<uint4>(st, L, AddU32x4{}, z,
+                      GcEmit{W.rowptr.p, W.col.p, W.val.p, W.nrow, reinterpret_cast<GcItem *>(P.gc_items.p), P.gc_ucol.p,
+                             reinterpret_cast<GcRec *>(P.gc_recs.p)}, s);
+    IB_CUDA(cudaStreamSynchronize(s));
+    P.gc = true;
 }
 
 // ---- pair-grouped column plan ------------------------------------------------------------------------------
@@ -644,6 +692,173 @@ __global__ void __launch_bounds__(XS_THREADS) spmm_xs_kernel(const XsArgs a)
     }
 }
 
+// ---- distinct-column group kernel: short-row matrices (IvE, IvA, EvA) --------------------------------------------
+// Unit = (item of gc_plan.cuh, tile of 64*NQ fields), owned by ONE WARP; lane l owns the double2 at fields
+// tile + 64q + 2l, q < NQ.  The X rows of the item's <= GC_S distinct columns are fetched ONCE, by 1-D bulk async copies
+// (cp.async.bulk, one per row, issued by lanes 0..nd-1) into a warp-private shared-memory slot table, together with the
+// item's records (value, slot, flags: 16 bytes per nonzero, prepared once per matrix); tables are double buffered: the
+// next unit lands (completing on a warp-private mbarrier) while the current one is processed.  The inner loop is a flat
+// walk over the records: broadcast-read a record, read the X row of its slot from shared memory, multiply-add, and on
+// the last record of a row store the row.  Record reads run two records ahead and X reads one record ahead of the
+// arithmetic.  Warps never synchronise with each other.
+// History: (1) one double2 per lane, values/slots broadcast by shuffles: bound by instruction issue (58 warp
+// instructions per nonzero and 64 fields); (2) NQ double2 per lane: 160 instructions per row and tile, every one
+// waiting ~6 cycles on the previous (3 shuffles + convergence checks per nonzero); (3) this one.
+// X traffic drops from one row per nonzero to one per distinct column (IvE 0.15x, IvA 0.06x at 5 km), which is what
+// bounded the row-streaming kernels: they ran at the L2 fabric rate (reads + writes ~ 8.4 TB/s), not at HBM's.
+// Rows are never split and are summed over ascending columns with mul-then-add: bit-identical to the oracle.
+struct GcArgs {
+    const int4 *items;
+    const int32_t *ucol;
+    const int4 *recs;
+    int64_t nitems;
+    int ntile;
+    const double *X;
+    int64_t ldx;
+    int nvar;
+    double *Y;
+    int64_t ldy;
+    int row_lo, row_hi;
+};
+constexpr int GC_WARPS = 2;      // warps per CTA (independent; a CTA is only a container for shared memory)
+constexpr int GC_RECBUF = (GC_MAXREC + 2) * 16;     // record table of one buffer (+2: the prefetch overruns)
+
+template <int NQ>
+constexpr size_t gc_smem_bytes() { return (size_t)GC_WARPS * (2 * (GC_S * 64 * NQ * 8 + GC_RECBUF) + 16); }
+
+template <int NQ>
+__global__ void __launch_bounds__(GC_WARPS * 32) spmm_gc_kernel(const GcArgs a)
+{
+    constexpr int TW = 64 * NQ;                        // fields per tile
+    constexpr uint32_t ROWB = TW * 8;                  // bytes per slot
+    constexpr uint32_t BUFB = GC_S * ROWB + GC_RECBUF; // one buffer: slot table + record table
+    extern __shared__ __align__(128) unsigned char gc_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *buf = gc_raw + (size_t)warp * (2 * BUFB);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(gc_raw + (size_t)GC_WARPS * (2 * BUFB)) + 2 * warp;
+    const unsigned FULL = 0xffffffffu;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // record of a unit: the item and (lanes 0..GC_S-1) its distinct columns.  Nothing here waits for a load: the
+    // row-block test is applied where the record is used.
+    auto load_item = [&](int64_t item, int4 &it, int &uc) {
+        it = make_int4(0, 0, 0, 0);
+        uc = -1;
+        if (item < a.nitems) {
+            it = __ldg(a.items + item);
+            if (lane < GC_S) uc = __ldg(a.ucol + item * GC_S + lane);
+        }
+    };
+    auto in_block = [&](const int4 &it) { return it.x >= a.row_lo && it.x < a.row_hi; };
+    // X rows and records of a unit -> buffer b.  The buffer was last read by this warp two units ago (program order +
+    // __syncwarp); units outside the row block fetch nothing.
+    auto issue = [&](int tile, const int4 &it, int uc, int b) {
+        const bool ok = in_block(it);
+        const int f0 = tile * TW;
+        const uint32_t tb = (uint32_t)min(TW, a.nvar - f0) * 8u;
+        const uint32_t rb = ok ? (uint32_t)(it.z - it.y) * 16u : 0u;
+        const bool mine = ok && uc >= 0;                     // lanes >= GC_S carry uc = -1
+        const int nd = __popc(__ballot_sync(FULL, mine));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic reads of the buffer before async writes
+        __syncwarp();
+        unsigned char *dst = buf + (size_t)b * BUFB;
+        if (lane == 0) {
+            if (rb + nd > 0) mbar_expect_tx(bar + b, tb * (uint32_t)nd + rb);
+            else mbar_arrive(bar + b);
+        }
+        __syncwarp();
+        if (mine) bulk_g2s(dst + (size_t)lane * ROWB, a.X + (int64_t)uc * a.ldx + f0, tb, bar + b);
+        if (lane == GC_S && rb > 0) bulk_g2s(dst + GC_S * ROWB, a.recs + it.y, rb, bar + b);
+    };
+
+    // unit u = item * ntile + tile; this warp owns u = gw, gw + nw, ...: (item, tile) advance by (dq, dr) with a carry
+    const int64_t nw = (int64_t)gridDim.x * GC_WARPS;
+    const int64_t gw = (int64_t)blockIdx.x * GC_WARPS + warp;
+    const int dq = (int)(nw / a.ntile), dr = (int)(nw % a.ntile);
+    auto advance = [&](int64_t &item, int &tile) {
+        item += dq; tile += dr;
+        if (tile >= a.ntile) { tile -= a.ntile; ++item; }
+    };
+    int64_t item_c = gw / a.ntile;
+    int tile_c = (int)(gw % a.ntile);
+    int64_t item_n = item_c, item_n2;
+    int tile_n = tile_c, tile_n2;
+    advance(item_n, tile_n);
+    item_n2 = item_n; tile_n2 = tile_n;
+    advance(item_n2, tile_n2);
+    int4 itc, itn, itn2;
+    int ucc, ucn, ucn2;
+    load_item(item_c, itc, ucc);
+    load_item(item_n, itn, ucn);
+    int b = 0;
+    uint32_t phase = 0;                                      // bit b: parity to wait for on bar[b]
+    if (item_c < a.nitems) issue(tile_c, itc, ucc, 0);
+    while (item_c < a.nitems) {
+        // prefetch: tables of the next unit, item record of the one after
+        if (item_n < a.nitems) issue(tile_n, itn, ucn, b ^ 1);
+        load_item(item_n2, itn2, ucn2);
+        // this unit's tables have landed?
+        mbar_wait(bar + b, (phase >> b) & 1u);
+        phase ^= 1u << b;
+        const int n = in_block(itc) ? itc.z - itc.y : 0;
+        const int f0 = tile_c * TW;
+        const int nq = min(NQ, (a.nvar - f0 + 63) >> 6);            // live 64-field groups of this tile
+        const bool last_live = f0 + 64 * (nq - 1) + 2 * lane < a.nvar;   // ragged last group
+        const double2 *xb = reinterpret_cast<const double2 *>(buf + (size_t)b * BUFB) + lane;
+        const int4 *rec = reinterpret_cast<const int4 *>(buf + (size_t)b * BUFB + GC_S * ROWB);
+        double2 *yp = reinterpret_cast<double2 *>(a.Y + (int64_t)itc.x * a.ldy + f0) + lane;
+        const int64_t ystep = a.ldy / 2;
+        double2 acc[NQ], x0[NQ], x1[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[q] = make_double2(0.0, 0.0);
+        int4 r0 = rec[0], r1 = rec[1];
+        {
+            const double2 *xr = xb + (r0.z & (GC_S - 1)) * (TW / 2);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x0[q] = xr[q * 32];
+        }
+        for (int k = 0; k < n; ++k) {
+            const int4 r2 = rec[k + 2];
+            {
+                const double2 *xr = xb + (r1.z & (GC_S - 1)) * (TW / 2);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) x1[q] = xr[q * 32];
+            }
+            if (!(r0.w & (int)GC_ZERO)) {
+                const double v = __hiloint2double(r0.y, r0.x);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    acc[q].x = acc[q].x + v * x0[q].x;
+                    acc[q].y = acc[q].y + v * x0[q].y;
+                }
+            }
+            if (r0.w & (int)GC_LAST) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    if (q < nq - 1 || (q == nq - 1 && last_live)) yp[q * 32] = acc[q];
+                    acc[q] = make_double2(0.0, 0.0);
+                }
+                yp += ystep;
+            }
+            r0 = r1; r1 = r2;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x0[q] = x1[q];
+        }
+        __syncwarp();
+        itc = itn; itn = itn2;
+        ucn = ucn2;
+        item_c = item_n; tile_c = tile_n;
+        item_n = item_n2; tile_n = tile_n2;
+        advance(item_n2, tile_n2);
+        b ^= 1;
+    }
+}
+
 // ---- plain-load fallback (small / odd nvar, unaligned buffers) ---------------------------------------------
 // A group of L lanes (power of two) owns one (item, field-tile) unit; lane fl owns VEC consecutive fields.
 template <int VEC>
@@ -893,6 +1108,34 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&max_smem_xs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         IB_CUDA(cudaFuncSetAttribute(spmm_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_xs));
+    }
+    // distinct-column groups: every row has <= GC_S nonzeros (IvE, IvA, EvA); variant 5 forces, others forbid
+    static const int gc_nq = getenv("IB_GC_NQ") ? atoi(getenv("IB_GC_NQ")) : 4;
+    static const int gc_wps = getenv("IB_GC_WPS") ? atoi(getenv("IB_GC_WPS")) : 0;          // warps per SM (0: all that fit)
+    if (P.gc && vec2 && nvar >= 32 && (variant == 0 || variant == 5)) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<4>()));
+            IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<2>()));
+            attr_set = true;
+        }
+        const int nq = (gc_nq == 2 || nvar <= 128) ? 2 : 4;
+        const int tw = 64 * nq;
+        const int ntile = (nvar + tw - 1) / tw;
+        GcArgs a{P.gc_items.p, P.gc_ucol.p, P.gc_recs.p, P.gc_nitems, ntile, dX, ldx, nvar, dY, ldy, rlo, rhi};
+        const size_t smem = nq == 4 ? gc_smem_bytes<4>() : gc_smem_bytes<2>();
+        int occ = 0;
+        if (nq == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_gc_kernel<4>, GC_WARPS * 32, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_gc_kernel<2>, GC_WARPS * 32, smem);
+        occ = std::max(occ, 1);
+        if (gc_wps > 0) occ = std::max(1, std::min(occ, gc_wps / GC_WARPS));
+        const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(cdiv(a.nitems * ntile, GC_WARPS), (int64_t)sm_count() * occ));
+        if (a.nitems > 0) {
+            if (nq == 4) spmm_gc_kernel<4><<<(unsigned)nblk, GC_WARPS * 32, smem, s>>>(a);
+            else spmm_gc_kernel<2><<<(unsigned)nblk, GC_WARPS * 32, smem, s>>>(a);
+            IB_LAUNCHED();
+        }
+        return;
     }
     // X-stationary path: tall matrix, few columns, no long rows (variant 3 forces it, 4 forbids it)
     if (vec2 && !ranged && variant != 1 && variant != 2 && variant != 4 && W.ncol > 0 && W.nrow >= 8 * W.ncol && P.max_row_len <= 256 && nvar >= 8 &&

@@ -91,6 +91,12 @@ struct ApplyPlan {
     DBuf<double> pv0, pv1;   // values of the column's first / second nonzero (0 if none)
     DBuf<int32_t> fx_ptr;    // [nrow+1] partial slots of each output row ...
     DBuf<uint32_t> fx_slot;  // ... in a fixed order
+    // distinct-column groups (matrices whose rows all have <= GC_S nonzeros, e.g. IvE, IvA): see gc_plan.cuh
+    bool gc = false;
+    int64_t gc_nitems = 0;
+    DBuf<int4> gc_items;     // (first_row, record_begin, record_end, -(rows in group))
+    DBuf<int32_t> gc_ucol;   // [gc_nitems][GC_S] distinct columns of the group (-1 = unused)
+    DBuf<int4> gc_recs;      // GcRec (value, slot, flags) per nonzero in row order, one dummy per empty row
 };
 
 // linear::Weighted_Eigen: CSR matrix (rows = output space) + weights + dims.

@@ -52,6 +52,49 @@ def test_apply_cfg2_bitexact_short_rows(cfg2):
         assert np.all(np.abs(lhs - rhs) <= 1e-12 * scale), spec
 
 
+def seq_rows_reference(M, X):
+    """Y = M X with every row summed over ascending columns, one mul and one add at a time (no fma): the order of
+    Eigen's column-major sparse * dense (and of the oracle).  M: (rowptr, col, val) CSR, X: [ncol, nvar]."""
+    rowptr, col, val = M
+    n = np.diff(rowptr)
+    Y = np.zeros((len(n), X.shape[1]))
+    for k in range(int(n.max()) if len(n) else 0):
+        rows = np.nonzero(n > k)[0]
+        j = rowptr[rows] + k
+        Y[rows] = Y[rows] + val[j, None] * X[col[j]]
+    return Y
+
+
+@pytest.mark.parametrize("spec", ["IvE", "IvA", "EvA"])
+@pytest.mark.parametrize("nvar", [32, 64, 100, 200, 300, 512])
+def test_apply_distinct_column_groups_bitexact(cfg2, spec, nvar):
+    """spmm_gc_kernel (rows of <= 8 nonzeros grouped by their distinct columns, every X row fetched once per group):
+    full and partial 64-field slices and a padded leading dimension.  Bit-identical to the sequential row sums over
+    the matrix's own values, and (IvE, IvA: values bit-equal to the oracle's) to the oracle's apply."""
+    import torch
+    go, gg = make_oracle(cfg2), make_gpu(cfg2)
+    em = cfg2["elevmask"][0]
+    Wg = gg.regrid_matrices(cfg2["sheets"][0].name, em, scale=True, correctA=True).matrix(spec)
+    X = np.random.default_rng(nvar).uniform(-1, 1, (nvar, Wg.shape[1]))
+    Yref = seq_rows_reference(Wg.to_csr(), np.ascontiguousarray(X.T)).T
+    Yg = Wg.apply(X)
+    assert np.array_equal(Yg, Yref)
+    Wo = go.matrix(0, em, spec, scale=True, correctA=True)
+    Yo = Wo.apply(X)
+    if spec != "EvA":      # EvA sums > 64 duplicates per entry with a warp: values within 1e-12, not bit-equal
+        assert np.array_equal(Yg, Yo)
+    assert np.all(np.abs(Yg - Yo) <= ref_tol(Wo, X))
+    ld = nvar + 6
+    Xd = torch.zeros((Wg.shape[1], ld), dtype=torch.float64, device="cuda")
+    Xd[:, :nvar] = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    Yd = torch.full((Wg.shape[0], ld), -7.0, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    Wg.apply_dev(Xd.data_ptr(), ld, nvar, Yd.data_ptr(), ld)
+    torch.cuda.synchronize()
+    Yh = Yd.cpu().numpy()
+    assert np.array_equal(Yh[:, :nvar].T, Yref) and np.all(Yh[:, nvar:] == -7.0)
+
+
 def test_apply_M_sparse_and_weights(cfg1):
     go, gg = make_oracle(cfg1), make_gpu(cfg1)
     sh = cfg1["sheets"][0]
