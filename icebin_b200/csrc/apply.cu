@@ -156,11 +156,14 @@ static void make_gc_plan(Weighted &W, cudaStream_t s)
     uint4 tot;
     IB_CUDA(cudaMemcpyAsync(&tot, st.total.p, sizeof tot, cudaMemcpyDeviceToHost, s));
     IB_CUDA(cudaStreamSynchronize(s));
+    if ((int64_t)tot.y != W.nnz) return;          // empty rows (dummy records): left to the other kernels
     P.gc_nitems = tot.x;
     P.gc_items.alloc((size_t)tot.x, s);
     P.gc_ucol.alloc((size_t)tot.x * GC_S, s);
     P.gc_recs.alloc((size_t)tot.y + 2, s);         // the kernel's record prefetch runs two entries ahead
     P.gc_recs.zero();
+    P.gc_counter.alloc(3, s);
+    P.gc_counter.zero();
     scan_apply<uint4>(st, L, AddU32x4{}, z,
                       GcEmit{W.rowptr.p, W.col.p, W.val.p, W.nrow, reinterpret_cast<GcItem *>(P.gc_items.p), P.gc_ucol.p,
                              reinterpret_cast<GcRec *>(P.gc_recs.p)}, s);
@@ -719,6 +722,7 @@ struct GcArgs {
     double *Y;
     int64_t ldy;
     int row_lo, row_hi;
+    unsigned long long *counter;     // [0] units handed out so far (never reset), [1] its value when this launch began, [2] warps done
 };
 constexpr int GC_WARPS = 2;      // warps per CTA (independent; a CTA is only a container for shared memory)
 constexpr int GC_RECBUF = (GC_MAXREC + 2) * 16;     // record table of one buffer (+2: the prefetch overruns)
@@ -743,13 +747,27 @@ __global__ void __launch_bounds__(GC_WARPS * 32) spmm_gc_kernel(const GcArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    const int64_t nunits = a.nitems * a.ntile;
 
+    // Units are handed out dynamically (items differ in size: 1..32 rows): unit u = item * ntile + tile.  The counter is
+    // read three units ahead of the arithmetic, so its latency is never waited for.
+    // the first three units of a warp are static; the counter hands out the rest.  It is never reset: the last warp
+    // to leave records where the next launch starts (so a captured graph can be replayed)
+    const int64_t nw = (int64_t)gridDim.x * GC_WARPS;
+    const unsigned long long cbase = a.counter[1] - 3ull * (unsigned long long)nw;
+    auto take_unit = [&]() -> unsigned long long {          // lane 0 holds the answer; broadcast where it is used
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(a.counter, 1ull) - cbase;
+        return u;
+    };
+    auto bcast = [&](unsigned long long u) -> int64_t { return (int64_t)__shfl_sync(FULL, u, 0); };
     // record of a unit: the item and (lanes 0..GC_S-1) its distinct columns.  Nothing here waits for a load: the
     // row-block test is applied where the record is used.
-    auto load_item = [&](int64_t item, int4 &it, int &uc) {
+    auto load_item = [&](int64_t u, int4 &it, int &uc) {
         it = make_int4(0, 0, 0, 0);
         uc = -1;
-        if (item < a.nitems) {
+        if (u < nunits) {
+            const int64_t item = (uint32_t)u / (uint32_t)a.ntile;        // nunits < 2^31 (checked by the host)
             it = __ldg(a.items + item);
             if (lane < GC_S) uc = __ldg(a.ucol + item * GC_S + lane);
         }
@@ -757,9 +775,9 @@ __global__ void __launch_bounds__(GC_WARPS * 32) spmm_gc_kernel(const GcArgs a)
     auto in_block = [&](const int4 &it) { return it.x >= a.row_lo && it.x < a.row_hi; };
     // X rows and records of a unit -> buffer b.  The buffer was last read by this warp two units ago (program order +
     // __syncwarp); units outside the row block fetch nothing.
-    auto issue = [&](int tile, const int4 &it, int uc, int b) {
+    auto issue = [&](int64_t u, const int4 &it, int uc, int b) {
         const bool ok = in_block(it);
-        const int f0 = tile * TW;
+        const int f0 = (int)((uint32_t)u % (uint32_t)a.ntile) * TW;
         const uint32_t tb = (uint32_t)min(TW, a.nvar - f0) * 8u;
         const uint32_t rb = ok ? (uint32_t)(it.z - it.y) * 16u : 0u;
         const bool mine = ok && uc >= 0;                     // lanes >= GC_S carry uc = -1
@@ -776,86 +794,84 @@ __global__ void __launch_bounds__(GC_WARPS * 32) spmm_gc_kernel(const GcArgs a)
         if (lane == GC_S && rb > 0) bulk_g2s(dst + GC_S * ROWB, a.recs + it.y, rb, bar + b);
     };
 
-    // unit u = item * ntile + tile; this warp owns u = gw, gw + nw, ...: (item, tile) advance by (dq, dr) with a carry
-    const int64_t nw = (int64_t)gridDim.x * GC_WARPS;
-    const int64_t gw = (int64_t)blockIdx.x * GC_WARPS + warp;
-    const int dq = (int)(nw / a.ntile), dr = (int)(nw % a.ntile);
-    auto advance = [&](int64_t &item, int &tile) {
-        item += dq; tile += dr;
-        if (tile >= a.ntile) { tile -= a.ntile; ++item; }
-    };
-    int64_t item_c = gw / a.ntile;
-    int tile_c = (int)(gw % a.ntile);
-    int64_t item_n = item_c, item_n2;
-    int tile_n = tile_c, tile_n2;
-    advance(item_n, tile_n);
-    item_n2 = item_n; tile_n2 = tile_n;
-    advance(item_n2, tile_n2);
+    int64_t u_c = (int64_t)blockIdx.x * GC_WARPS + warp, u_n = u_c + nw, u_n2 = u_n + nw;
+    unsigned long long raw_n3 = take_unit();
     int4 itc, itn, itn2;
     int ucc, ucn, ucn2;
-    load_item(item_c, itc, ucc);
-    load_item(item_n, itn, ucn);
+    load_item(u_c, itc, ucc);
+    load_item(u_n, itn, ucn);
     int b = 0;
     uint32_t phase = 0;                                      // bit b: parity to wait for on bar[b]
-    if (item_c < a.nitems) issue(tile_c, itc, ucc, 0);
-    while (item_c < a.nitems) {
-        // prefetch: tables of the next unit, item record of the one after
-        if (item_n < a.nitems) issue(tile_n, itn, ucn, b ^ 1);
-        load_item(item_n2, itn2, ucn2);
+    if (u_c < nunits) issue(u_c, itc, ucc, 0);
+    while (u_c < nunits) {
+        // prefetch: tables of the next unit, item record of the one after, unit number of the one after that
+        if (u_n < nunits) issue(u_n, itn, ucn, b ^ 1);
+        load_item(u_n2, itn2, ucn2);
+        const int64_t u_n3 = bcast(raw_n3);
+        raw_n3 = take_unit();
         // this unit's tables have landed?
         mbar_wait(bar + b, (phase >> b) & 1u);
         phase ^= 1u << b;
         const int n = in_block(itc) ? itc.z - itc.y : 0;
-        const int f0 = tile_c * TW;
+        const int f0 = (int)((uint32_t)u_c % (uint32_t)a.ntile) * TW;
         const int nq = min(NQ, (a.nvar - f0 + 63) >> 6);            // live 64-field groups of this tile
         const bool last_live = f0 + 64 * (nq - 1) + 2 * lane < a.nvar;   // ragged last group
+        bool live[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) live[q] = q < nq - 1 || (q == nq - 1 && last_live);
         const double2 *xb = reinterpret_cast<const double2 *>(buf + (size_t)b * BUFB) + lane;
         const int4 *rec = reinterpret_cast<const int4 *>(buf + (size_t)b * BUFB + GC_S * ROWB);
         double2 *yp = reinterpret_cast<double2 *>(a.Y + (int64_t)itc.x * a.ldy + f0) + lane;
         const int64_t ystep = a.ldy / 2;
-        double2 acc[NQ], x0[NQ], x1[NQ];
+        double2 acc[NQ], xA[NQ], xB[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) acc[q] = make_double2(0.0, 0.0);
-        int4 r0 = rec[0], r1 = rec[1];
-        {
-            const double2 *xr = xb + (r0.z & (GC_S - 1)) * (TW / 2);
+        auto fetch = [&](double2(&x)[NQ], int slot) {
+            const double2 *xr = xb + (slot & (GC_S - 1)) * (TW / 2);
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) x0[q] = xr[q * 32];
-        }
-        for (int k = 0; k < n; ++k) {
-            const int4 r2 = rec[k + 2];
-            {
-                const double2 *xr = xb + (r1.z & (GC_S - 1)) * (TW / 2);
+            for (int q = 0; q < NQ; ++q) x[q] = xr[q * 32];
+        };
+        // branch-free: the row sum so far goes out through its own registers when the record closes its row (the
+        // accumulators are not written while a store still reads them), and the accumulators restart from zero
+        auto step = [&](const int4 &r, const double2(&x)[NQ]) {
+            const double v = __hiloint2double(r.y, r.x);
+            const bool last = (r.w & (int)GC_LAST) != 0;
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) x1[q] = xr[q * 32];
+            for (int q = 0; q < NQ; ++q) {
+                double2 t;
+                t.x = acc[q].x + v * x[q].x;
+                t.y = acc[q].y + v * x[q].y;
+                if (last && live[q]) yp[q * 32] = t;
+                acc[q].x = last ? 0.0 : t.x;
+                acc[q].y = last ? 0.0 : t.y;
             }
-            if (!(r0.w & (int)GC_ZERO)) {
-                const double v = __hiloint2double(r0.y, r0.x);
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    acc[q].x = acc[q].x + v * x0[q].x;
-                    acc[q].y = acc[q].y + v * x0[q].y;
-                }
-            }
-            if (r0.w & (int)GC_LAST) {
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    if (q < nq - 1 || (q == nq - 1 && last_live)) yp[q * 32] = acc[q];
-                    acc[q] = make_double2(0.0, 0.0);
-                }
-                yp += ystep;
-            }
-            r0 = r1; r1 = r2;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) x0[q] = x1[q];
+            yp += last ? ystep : 0;
+        };
+        // flat walk over the records, two per trip: a record names the slot of its successor, so the successor's X row
+        // is fetched (and the successor read) while the record itself is processed
+        int4 rA = rec[0], rB;
+        fetch(xA, rA.z);
+        for (int k = 0; k < n; k += 2) {
+            rB = rec[k + 1];
+            fetch(xB, rA.z >> 8);
+            step(rA, xA);
+            if (k + 1 >= n) break;
+            rA = rec[k + 2];
+            fetch(xA, rB.z >> 8);
+            step(rB, xB);
         }
         __syncwarp();
         itc = itn; itn = itn2;
         ucn = ucn2;
-        item_c = item_n; tile_c = tile_n;
-        item_n = item_n2; tile_n = tile_n2;
-        advance(item_n2, tile_n2);
+        u_c = u_n; u_n = u_n2; u_n2 = u_n3;
         b ^= 1;
+    }
+    if (lane == 0) {
+        __threadfence();
+        if (atomicAdd(a.counter + 2, 1ull) == (unsigned long long)nw - 1) {      // every other warp has taken its last unit
+            a.counter[1] = atomicAdd(a.counter, 0ull);
+            a.counter[2] = 0;
+        }
     }
 }
 
@@ -1110,29 +1126,30 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         IB_CUDA(cudaFuncSetAttribute(spmm_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_xs));
     }
     // distinct-column groups: every row has <= GC_S nonzeros (IvE, IvA, EvA); variant 5 forces, others forbid
-    static const int gc_nq = getenv("IB_GC_NQ") ? atoi(getenv("IB_GC_NQ")) : 4;
+    static const int gc_nq = getenv("IB_GC_NQ") ? atoi(getenv("IB_GC_NQ")) : 0;             // 0: by nvar
     static const int gc_wps = getenv("IB_GC_WPS") ? atoi(getenv("IB_GC_WPS")) : 0;          // warps per SM (0: all that fit)
-    if (P.gc && vec2 && nvar >= 32 && (variant == 0 || variant == 5)) {
+    if (P.gc && vec2 && nvar >= 32 && (variant == 0 || variant == 5) && P.gc_nitems * (int64_t)((nvar + 63) / 64) < (int64_t(1) << 31)) {
         static bool attr_set = false;
         if (!attr_set) {
             IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<4>()));
             IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<2>()));
+            IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<1>()));
             attr_set = true;
         }
-        const int nq = (gc_nq == 2 || nvar <= 128) ? 2 : 4;
+        int nq = nvar <= 64 ? 1 : 2;
+        if (gc_nq == 1 || gc_nq == 2 || gc_nq == 4) nq = gc_nq;
         const int tw = 64 * nq;
         const int ntile = (nvar + tw - 1) / tw;
-        GcArgs a{P.gc_items.p, P.gc_ucol.p, P.gc_recs.p, P.gc_nitems, ntile, dX, ldx, nvar, dY, ldy, rlo, rhi};
-        const size_t smem = nq == 4 ? gc_smem_bytes<4>() : gc_smem_bytes<2>();
+        GcArgs a{P.gc_items.p, P.gc_ucol.p, P.gc_recs.p, P.gc_nitems, ntile, dX, ldx, nvar, dY, ldy, rlo, rhi, P.gc_counter.p};
+        const size_t smem = nq == 4 ? gc_smem_bytes<4>() : nq == 2 ? gc_smem_bytes<2>() : gc_smem_bytes<1>();
+        auto kern = nq == 4 ? spmm_gc_kernel<4> : nq == 2 ? spmm_gc_kernel<2> : spmm_gc_kernel<1>;
         int occ = 0;
-        if (nq == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_gc_kernel<4>, GC_WARPS * 32, smem);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_gc_kernel<2>, GC_WARPS * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GC_WARPS * 32, smem);
         occ = std::max(occ, 1);
         if (gc_wps > 0) occ = std::max(1, std::min(occ, gc_wps / GC_WARPS));
         const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(cdiv(a.nitems * ntile, GC_WARPS), (int64_t)sm_count() * occ));
         if (a.nitems > 0) {
-            if (nq == 4) spmm_gc_kernel<4><<<(unsigned)nblk, GC_WARPS * 32, smem, s>>>(a);
-            else spmm_gc_kernel<2><<<(unsigned)nblk, GC_WARPS * 32, smem, s>>>(a);
+            kern<<<(unsigned)nblk, GC_WARPS * 32, smem, s>>>(a);
             IB_LAUNCHED();
         }
         return;

@@ -26,6 +26,8 @@ constexpr uint32_t GC_LAST = 1u; // record closes its row
 constexpr uint32_t GC_ZERO = 2u; // dummy record of an empty row (no arithmetic)
 
 struct GcItem { int32_t row, rbeg, rend, negrows; };     // same layout as the int4 items of the other plans
+// slot: bits 0-7 the record's own slot, bits 8-15 the slot of the NEXT record of the item (so that the kernel can fetch the
+// next record's X row without having read the next record)
 struct alignas(16) GcRec { double v; uint32_t slot, flags; };
 struct GcCount { uint32_t items, recs; };
 
@@ -85,7 +87,9 @@ IB_HD inline GcCount gc_block(const int32_t *rowptr, const int32_t *col, const d
                 for (int q = 0; q < nu; ++q) s = (ul[q] == c) ? (uint32_t)q : s;
                 GcRec rc;
                 rc.v = val[j]; rc.slot = s; rc.flags = (j + 1 == je) ? GC_LAST : 0u;
-                recs[rbase + nrec + (uint32_t)(j - jb)] = rc;
+                const uint32_t p = nrec + (uint32_t)(j - jb);
+                recs[rbase + p] = rc;
+                if (p > rec0) recs[rbase + p - 1].slot |= s << 8;       // previous record of the same item
             }
             if (je <= jb) {
                 GcRec rc;

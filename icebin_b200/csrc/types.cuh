@@ -97,6 +97,7 @@ struct ApplyPlan {
     DBuf<int4> gc_items;     // (first_row, record_begin, record_end, -(rows in group))
     DBuf<int32_t> gc_ucol;   // [gc_nitems][GC_S] distinct columns of the group (-1 = unused)
     DBuf<int4> gc_recs;      // GcRec (value, slot, flags) per nonzero in row order, one dummy per empty row
+    DBuf<unsigned long long> gc_counter;   // dynamic unit counter of the kernel (one apply at a time per matrix)
 };
 
 // linear::Weighted_Eigen: CSR matrix (rows = output space) + weights + dims.

@@ -49,11 +49,16 @@ extern "C" int gc_emul(const int32_t *rowptr, const int32_t *col, const double *
             } else
                 for (int j = rowptr[r]; j < rowptr[r + 1]; ++j, ++rec) {
                     const GcRec &rc = recs[rec];
-                    if (rc.v != val[j] || (int)rc.slot >= nu || ucol[(size_t)k * GC_S + rc.slot] != col[j]) return -9;
+                    if (rc.v != val[j] || (int)(rc.slot & 0xff) >= nu || ucol[(size_t)k * GC_S + (rc.slot & 0xff)] != col[j]) return -9;
+                    if ((rc.slot >> 16) != 0) return -9;
                     if (rc.flags != ((j + 1 == rowptr[r + 1]) ? GC_LAST : 0u)) return -10;
                 }
         }
         if (rec != it.rend) return -11;
+        for (int q = it.rbeg; q < it.rend; ++q) {       // next-slot links inside the item
+            const uint32_t want = q + 1 < it.rend ? (recs[q + 1].slot & 0xff) : 0u;
+            if (((recs[q].slot >> 8) & 0xff) != want) return -14;
+        }
         ndist += nu;
         next_row += nrows; next_rec = it.rend;
     }
@@ -70,12 +75,14 @@ extern "C" int gc_emul(const int32_t *rowptr, const int32_t *col, const double *
             }
             int64_t row = it.row;
             double acc = 0.0;
+            uint32_t sl = recs[it.rbeg].slot & 0xff;          // the kernel learns a record's slot from its predecessor
             for (int q = it.rbeg; q < it.rend; ++q) {
                 const GcRec &rc = recs[q];
                 if (!(rc.flags & GC_ZERO)) {
-                    const double t = rc.v * xs[rc.slot & (GC_S - 1)];
+                    const double t = rc.v * xs[sl & (GC_S - 1)];
                     acc = acc + t;
                 }
+                sl = (rc.slot >> 8) & 0xff;
                 if (rc.flags & GC_LAST) { Y[row * nvar + f] = acc; acc = 0.0; ++row; }
             }
             if (row != it.row - it.negrows) return -13;

@@ -95,6 +95,33 @@ def test_apply_distinct_column_groups_bitexact(cfg2, spec, nvar):
     assert np.array_equal(Yh[:, :nvar].T, Yref) and np.all(Yh[:, nvar:] == -7.0)
 
 
+def test_distinct_column_groups_graph_replay(cfg2):
+    """The group kernel hands its units out through a device counter that is never reset (the last warp records where
+    the next launch starts), so a captured apply can be replayed, mixed with eager applies and row blocks."""
+    import torch
+    gg = make_gpu(cfg2)
+    M = gg.regrid_matrices(cfg2["sheets"][0].name, cfg2["elevmask"][0], scale=True, correctA=True).matrix("IvE")
+    nvar = 192
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        X = torch.rand((M.shape[1], nvar), dtype=torch.float64, device="cuda")
+        Y0 = torch.empty((M.shape[0], nvar), dtype=torch.float64, device="cuda")
+        Y = torch.zeros_like(Y0)
+        M.apply_dev(X.data_ptr(), nvar, nvar, Y0.data_ptr(), nvar, True, st.cuda_stream)        # builds the plan
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            M.apply_dev(X.data_ptr(), nvar, nvar, Y.data_ptr(), nvar, True, st.cuda_stream)
+            M.apply_dev(X.data_ptr(), nvar, nvar, Y.data_ptr(), nvar, True, st.cuda_stream)
+        for rep in range(3):
+            Y.zero_()
+            g.replay()
+            M.apply_rows_dev(X.data_ptr(), nvar, nvar, Y.data_ptr(), nvar, 64, 4096, st.cuda_stream)
+            st.synchronize()
+            assert torch.equal(Y, Y0), rep
+            X.mul_(0.5); Y0.mul_(0.5)        # exact scaling: the replay must read the new X
+
+
 def test_apply_M_sparse_and_weights(cfg1):
     go, gg = make_oracle(cfg1), make_gpu(cfg1)
     sh = cfg1["sheets"][0]
