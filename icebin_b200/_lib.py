@@ -19,6 +19,10 @@ SIGNATURES = {
     "ib_device_count": (C.c_int, []),
     "ib_set_device": (C.c_int, [C.c_int]),
     "ib_launch_count": (i64, []),
+    "ib_dev_alloc": (C.c_int, [PP, i64]),
+    "ib_dev_free": (None, [vp]),
+    "ib_dev_upload": (C.c_int, [vp, vp, i64]),
+    "ib_dev_download": (C.c_int, [vp, vp, i64]),
     "ib_gcm_create": (C.c_int, [PP, i64, i32, vp, vp, i32, vp, C.c_int]),
     "ib_gcm_free": (None, [vp]),
     "ib_gcm_add_sheet": (C.c_int, [vp, cp, i64, i32, vp, vp, vp, i64, vp, vp, vp, C.c_int]),
@@ -60,6 +64,8 @@ SIGNATURES = {
     "ib_w_apply_weight": (C.c_int, [vp, C.c_int, vp, i32, vp]),
     "ib_coo_matvec": (C.c_int, [vp, vp, C.c_int, i64, i64, i64, vp, vp, vp]),
     "ib_multivec_to_dense": (C.c_int, [i64, vp, vp, vp, i32, i64, f64, vp, vp]),
+    "ib_vartrans_dev": (C.c_int, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
+    "ib_e1ve0c": (i64, [i32, vp, vp, i64, vp, vp, vp]),
     "ib_merge_pack_dev": (C.c_int, [vp, i64, i32, vp, i64, vp, vp]),
     "ib_merge_unpack_dev": (C.c_int, [vp, i64, i32, i64, vp, vp, vp, vp, vp]),
     "ib_hntr_create": (C.c_int, [PP, C.c_int, C.c_int, f64, f64, C.c_int, C.c_int, f64, f64, f64]),

@@ -14,7 +14,8 @@ import numpy as np
 from ._lib import IceBinError, check, lib, vp
 
 __all__ = ["GCMRegridder", "RegridMatrices", "Weighted", "SparseSet", "HntrSpec", "Hntr", "IceBinError",
-           "coo_matvec", "multivec_to_dense", "device_count", "launch_count", "apply_many", "apply_many_dev"]
+           "coo_matvec", "multivec_to_dense", "device_count", "launch_count", "apply_many", "apply_many_dev",
+           "vartrans_dev", "vartrans", "e1ve0c"]
 
 
 def _p(a):
@@ -431,6 +432,49 @@ def coo_matvec(yy, xx, ignore_nan, nrow, ncol, row, col, data):
     assert yy.dtype == np.float64 and yy.flags.c_contiguous
     check(lib().ib_coo_matvec(_p(yy), _p(xx), int(ignore_nan), nrow, ncol, len(data), _p(row), _p(col), _p(data)))
     return yy
+
+
+def _csc_arrays(M):
+    import scipy.sparse
+    Mc = scipy.sparse.csc_matrix(M)
+    Mc.sort_indices()
+    return Mc.shape, _c(Mc.indptr, np.int32), _c(Mc.indices, np.int32), _c(Mc.data, np.float64)
+
+
+def vartrans_dev(dO_ptr, ldo, ncell, M, b, dZ_ptr, ldz, stream=0):
+    """Z = O * M + b on device-resident cell-major fields (IceCoupler.cpp:203-252, :404-446).  M: [nin, nout] sparse
+    (the transposed VarTransformer matrix), b: [nout]."""
+    (nin, nout), cp_, row, val = _csc_arrays(M)
+    b = _c(b, np.float64)
+    assert b.shape == (nout,)
+    check(lib().ib_vartrans_dev(vp(dO_ptr), ldo, ncell, nin, nout, _p(cp_), _p(row), _p(val), _p(b), vp(dZ_ptr), ldz,
+                                vp(stream) if stream else None))
+
+
+def vartrans(O, M, b):
+    """Host-array convenience around vartrans_dev (torch is only the device container).  O: [ncell, nin] -> [ncell, nout]."""
+    import torch
+    O = _c(np.atleast_2d(O), np.float64)
+    nout = M.shape[1]
+    dO = torch.from_numpy(O).cuda()
+    dZ = torch.empty((O.shape[0], nout), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    vartrans_dev(dO.data_ptr(), O.shape[1], O.shape[0], M, b, dZ.data_ptr(), nout)
+    return dZ.cpu().numpy()
+
+
+def e1ve0c(XuE1s, XuE0s, nE):
+    """e1ve0::compute_E1vE0c (e1ve0.cpp:55-106): correction matrix between the elevation-class spaces of two coupling
+    steps.  XuE*: per-sheet "XvE" matrices (scale=False, correctA=True, identity X dim).  Returns (iE1, iE0, val) in sparse
+    E indices, sorted by (iE1, iE0)."""
+    n = len(XuE1s)
+    assert n == len(XuE0s) and n > 0
+    a = (vp * n)(*[w._h for w in XuE1s]); b = (vp * n)(*[w._h for w in XuE0s])
+    cnt = lib().ib_e1ve0c(n, a, b, int(nE), None, None, None)
+    check(min(cnt, 0))
+    r = np.zeros(cnt, np.int64); c = np.zeros(cnt, np.int64); v = np.zeros(cnt)
+    check(min(lib().ib_e1ve0c(n, a, b, int(nE), _p(r), _p(c), _p(v)), 0))
+    return r, c, v
 
 
 def multivec_to_dense(index, weights, vals, nE, fill=np.nan):

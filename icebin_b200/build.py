@@ -20,6 +20,7 @@ UNITS = {
     "build.cu": ["-fmad=false"],
     "apply.cu": ["-fmad=false"],
     "smooth.cu": ["-fmad=false"],
+    "couple.cu": ["-fmad=false"],
     "hntr.cu": [],
     "merge.cu": [],
     "capi.cu": [],

@@ -35,7 +35,7 @@ namespace ib {
 
 constexpr int APPLY_CHUNK = 32;
 constexpr int GROUP_ROWS = 32;
-static int pair_chunk() { static int v = getenv("IB_PAIR_CHUNK") ? atoi(getenv("IB_PAIR_CHUNK")) : 32; return v; }
+static int pair_chunk() { static int v = getenv("IB_PAIR_CHUNK") ? atoi(getenv("IB_PAIR_CHUNK")) : 48; return v; }
 
 // ---- plan -----------------------------------------------------------------------------------------------
 // item = (first_row, nnz_begin, nnz_end, w):  w >= 0: chunk of a long row, w = partial slot

@@ -59,6 +59,12 @@ void hntr_dims(Hntr const &, int *);
 void hntr_regrid_dev(Hntr &, const double *, double, double, const void *, int, double *, bool, cudaStream_t);
 int64_t hntr_matrix(Hntr &, double, int64_t *, int64_t *, double *, cudaStream_t);
 
+// couple.cu
+void vartrans_dev(const double *, int64_t, int64_t, int, int, const int32_t *, const int32_t *, const double *, const double *, double *,
+                  int64_t, cudaStream_t);
+void e1ve0c(int, Weighted *const *, Weighted *const *, int64_t, std::vector<int64_t> &, std::vector<int64_t> &, std::vector<double> &,
+            cudaStream_t);
+
 // merge.cu
 void merge_pack(const double *, int64_t, int, const int32_t *, int64_t, double *, cudaStream_t);
 void merge_unpack(double *, int64_t, int, int64_t, const int32_t *, const double *, const double *, const double *, cudaStream_t);
@@ -147,6 +153,46 @@ int ib_set_device(int device)
     IB_CATCH
 }
 int64_t ib_launch_count(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------------------------------- device buffers
+int ib_dev_alloc(void **out, int64_t bytes)
+{
+    IB_TRY
+    if (!out || bytes < 0) fail(IB_ERR_ARG, "ib_dev_alloc: bad argument");
+    ensure_device();
+    *out = nullptr;
+    cudaStream_t s = default_stream();
+    if (bytes > 0) IB_CUDA(cudaMallocAsync(out, (size_t)bytes, s));
+    IB_CUDA(cudaStreamSynchronize(s));
+    return IB_OK;
+    IB_CATCH
+}
+void ib_dev_free(void *p)
+{
+    if (p) cudaFreeAsync(p, default_stream());
+}
+int ib_dev_upload(void *dst_dev, const void *src_host, int64_t bytes)
+{
+    IB_TRY
+    if (bytes < 0 || (bytes > 0 && (!dst_dev || !src_host))) fail(IB_ERR_ARG, "ib_dev_upload: bad argument");
+    ensure_device();
+    cudaStream_t s = default_stream();
+    if (bytes > 0) IB_CUDA(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, s));
+    IB_CUDA(cudaStreamSynchronize(s));
+    return IB_OK;
+    IB_CATCH
+}
+int ib_dev_download(void *dst_host, const void *src_dev, int64_t bytes)
+{
+    IB_TRY
+    if (bytes < 0 || (bytes > 0 && (!dst_host || !src_dev))) fail(IB_ERR_ARG, "ib_dev_download: bad argument");
+    ensure_device();
+    cudaStream_t s = default_stream();
+    if (bytes > 0) IB_CUDA(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, s));
+    IB_CUDA(cudaStreamSynchronize(s));
+    return IB_OK;
+    IB_CATCH
+}
 
 // ---------------------------------------------------------------------------------------- GCMRegridder
 int ib_gcm_create(ib_gcm **out, int64_t nA, int32_t n_real, const int64_t *dimA, const double *native_area, int32_t nhc,
@@ -674,6 +720,42 @@ int ib_multivec_to_dense(int64_t n, const int64_t *index, const double *weights,
         for (int64_t i = 0; i < nE; ++i) if (std::isnan(d[i])) d[i] = fill;
     }
     return IB_OK;
+    IB_CATCH
+}
+
+// ---------------------------------------------------------------------------------------- coupling step
+int ib_vartrans_dev(const double *dO, int64_t ldo, int64_t ncell, int32_t nin, int32_t nout, const int32_t *colptr, const int32_t *row,
+                    const double *val, const double *b, double *dZ, int64_t ldz, void *stream)
+{
+    IB_TRY
+    if (!colptr || !b || (ncell > 0 && (!dO || !dZ)) || nout <= 0 || (colptr[nout] > 0 && (!row || !val)))
+        fail(IB_ERR_ARG, "ib_vartrans_dev: bad argument");
+    vartrans_dev(dO, ldo, ncell, nin, nout, colptr, row, val, b, dZ, ldz, stream ? (cudaStream_t)stream : default_stream());
+    return IB_OK;
+    IB_CATCH
+}
+
+int64_t ib_e1ve0c(int32_t nsheet, const ib_weighted *const *XuE1, const ib_weighted *const *XuE0, int64_t nE, int64_t *rows,
+                  int64_t *cols, double *vals)
+{
+    static thread_local std::vector<int64_t> r, c;
+    static thread_local std::vector<double> v;
+    IB_TRY
+    if (nsheet <= 0 || !XuE1 || !XuE0) fail(IB_ERR_ARG, "ib_e1ve0c: bad argument");
+    if (!rows) {
+        std::vector<Weighted *> a((size_t)nsheet), b((size_t)nsheet);
+        for (int i = 0; i < nsheet; ++i) {
+            if (!XuE1[i] || !XuE0[i]) fail(IB_ERR_ARG, "ib_e1ve0c: null matrix");
+            a[i] = XuE1[i]->w.get(); b[i] = XuE0[i]->w.get();
+        }
+        e1ve0c(nsheet, a.data(), b.data(), nE, r, c, v, default_stream());
+        return (int64_t)r.size();
+    }
+    if (!cols || !vals) fail(IB_ERR_ARG, "ib_e1ve0c: bad argument");
+    std::copy(r.begin(), r.end(), rows);
+    std::copy(c.begin(), c.end(), cols);
+    std::copy(v.begin(), v.end(), vals);
+    return (int64_t)r.size();
     IB_CATCH
 }
 

@@ -52,6 +52,14 @@ int ib_set_device(int device);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 int64_t ib_launch_count(void);
 
+/* Device buffers for hosts that do not link the CUDA runtime themselves (include/icebin/coupler_b200.hpp keeps the
+ * coupling fields in HBM between the variable transformation and the regrid applies).  Stream-ordered on the library's
+ * own stream; upload/download return when the copy is complete. */
+int ib_dev_alloc(void **out, int64_t bytes);
+void ib_dev_free(void *p);
+int ib_dev_upload(void *dst_dev, const void *src_host, int64_t bytes);
+int ib_dev_download(void *dst_host, const void *src_dev, int64_t bytes);
+
 /* ---- GCMRegridder_Standard ------------------------------------------------------------------------- */
 /* GCMRegridder_Standard::init(AbbrGrid&&, hcdefs, indexingHC, correctA)  GCMRegridder.hpp:346-352,
  * with indexingHC fixed to {A,HC} / HC slowest, iE = ihc*nA + iA          pylib/icebin_cython.cpp:56-73.
@@ -162,6 +170,25 @@ int ib_merge_pack_dev(const double *dY, int64_t ldy, int32_t nvar, const int32_t
                       void *stream);
 int ib_merge_unpack_dev(double *dY, int64_t ldy, int32_t nvar, int64_t nrow, const int32_t *d_slot_of_row,
                         const double *d_buf, const double *d_wtot, const double *d_wlocal, void *stream);
+
+/* ---- Coupling step, regridding side (callers of the path: SURVEY 8f rank 2) ---------------------------- */
+/* Variable/unit transformation in front of a regrid apply:  Z = O * M + b.replicate(ncell, 1)
+ *   gcm -> ice: ice_ivalsI = IvE0 * (gcm_ovalsE0 * ivg.M + ivg.b)        IceCoupler.cpp:203-252
+ *   ice -> gcm: gcm_ivalsX = X1vI * (ice_ovalsI * gvi.M + gvi.b)         IceCoupler.cpp:404-446
+ * dO: [ncell][ldo] cell-major device fields (nin variables), dZ: [ncell][ldz] (nout variables).  M is the transposed
+ * VarTransformer matrix (apply_scalars(scalars, 'T')), column-major sparse [nin x nout] on the HOST: colptr[nout+1],
+ * row[nnz], val[nnz]; b[nout].  Structural zeros are never multiplied (a NaN only reaches the outputs that name it).
+ * Synchronises `stream` (the small host arrays are staged). */
+int ib_vartrans_dev(const double *dO, int64_t ldo, int64_t ncell, int32_t nin, int32_t nout, const int32_t *colptr,
+                    const int32_t *row, const double *val, const double *b, double *dZ, int64_t ldz, void *stream);
+
+/* e1ve0::compute_E1vE0c(XuE1s, XuE0s, nE, areaX)   e1ve0.cpp:55-106, call site GCMCoupler.cpp:488-515.
+ * XuE1[i], XuE0[i]: the sheet's "XvE" matrices (scale = 0, correctA = 1, identity X dim) of this and of the previous
+ * coupling step; the sparsify() of GCMCoupler.cpp:388-449 is done inside.  Result: tuples (iE1, iE0, value) in SPARSE
+ * E indices, sorted by (iE1, iE0), duplicates summed (consolidate, e1ve0.cpp:32-52).
+ * Call with rows == NULL to get the entry count (the result is kept until the next call on this thread). */
+int64_t ib_e1ve0c(int32_t nsheet, const ib_weighted *const *XuE1, const ib_weighted *const *XuE0, int64_t nE, int64_t *rows,
+                  int64_t *cols, double *vals);
 
 /* ---- Hntr ------------------------------------------------------------------------------------------ */
 /* Hntr(yp17, Bspec, Aspec, DATMIS); HntrSpec(im, jm, offi, dlat[minutes])   hntr.cpp:63-82, GridSpec.hpp:143-170 */

@@ -746,6 +746,103 @@ static void hntr_matrix(Hntr const &h, double R2, std::vector<long> &rows, std::
         });
 }
 
+// ---------------------------------------------------------------------------------------
+// Coupling step, regridding side.
+//
+// Variable transformation in front of a regrid (IceCoupler.cpp:203-252, :404-446):
+//   Z = O * M + b.replicate(n,1)   with O dense [ncell x nin], M sparse col-major [nin x nout], b [nout].
+// Eigen's dense*sparse walks the stored entries of each column of M in order; structural zeros are never touched.
+static void vartrans(const double *O, long ncell, int nin, int nout, const int *colptr, const int *row, const double *val,
+                     const double *b, double *Z)
+{
+    for (int k = 0; k < nout; ++k)
+        for (int j = colptr[k]; j < colptr[k + 1]; ++j)
+            if (row[j] < 0 || row[j] >= nin) fail("vartrans: row index out of range");
+    for (long i = 0; i < ncell; ++i)
+        for (int k = 0; k < nout; ++k) {
+            double acc = 0.0;
+            for (int j = colptr[k]; j < colptr[k + 1]; ++j) acc += O[i * nin + row[j]] * val[j];
+            Z[i * nout + k] = acc + b[k];
+        }
+}
+
+static Csc transpose(Csc const &M)
+{
+    Csc T;
+    T.nrow = M.ncol; T.ncol = M.nrow;
+    T.ptr.assign(M.nrow + 1, 0);
+    for (int r : M.row) T.ptr[r + 1]++;
+    for (int i = 0; i < M.nrow; ++i) T.ptr[i + 1] += T.ptr[i];
+    T.row.resize(M.row.size()); T.val.resize(M.val.size());
+    std::vector<int> fill(T.ptr.begin(), T.ptr.end() - 1);
+    for (int j = 0; j < M.ncol; ++j)
+        for (int p = M.ptr[j]; p < M.ptr[j + 1]; ++p) { int q = fill[M.row[p]]++; T.row[q] = j; T.val[q] = M.val[p]; }
+    return T;
+}
+// Eigen sparse - sparse (CwiseBinaryOp<scalar_difference_op>): union of the patterns; a - 0 and 0 - b where one is missing.
+static Csc sub(Csc const &A, Csc const &B)
+{
+    if (A.nrow != B.nrow || A.ncol != B.ncol) fail("sub: shapes differ");
+    Csc C;
+    C.nrow = A.nrow; C.ncol = A.ncol;
+    C.ptr.assign(A.ncol + 1, 0);
+    for (int j = 0; j < A.ncol; ++j) {
+        int p = A.ptr[j], q = B.ptr[j];
+        const int pe = A.ptr[j + 1], qe = B.ptr[j + 1];
+        while (p < pe || q < qe) {
+            if (q >= qe || (p < pe && A.row[p] < B.row[q])) { C.row.push_back(A.row[p]); C.val.push_back(A.val[p] - 0.); ++p; }
+            else if (p >= pe || B.row[q] < A.row[p]) { C.row.push_back(B.row[q]); C.val.push_back(0. - B.val[q]); ++q; }
+            else { C.row.push_back(A.row[p]); C.val.push_back(A.val[p] - B.val[q]); ++p; ++q; }
+        }
+        C.ptr[j + 1] = (int)C.row.size();
+    }
+    return C;
+}
+// GCMCoupler.cpp:388-449 sparsify(XuE, {ID, TO_SPARSE}, {nX, -1}): rows keep their (identity) ids, columns and Mw go
+// to sparse E indexing.
+struct SparsifiedX { Csc M; std::vector<double> wM, Mw; };
+static SparsifiedX sparsify_XuE(Weighted const &W, long nE)
+{
+    SparsifiedX S;
+    std::vector<Trip> t;
+    for (int j = 0; j < W.M.ncol; ++j)
+        for (int p = W.M.ptr[j]; p < W.M.ptr[j + 1]; ++p) t.push_back(Trip{W.M.row[p], (int)W.dims[1].to_s[j], W.M.val[p]});
+    S.M = assemble(t, W.M.nrow, (int)nE);
+    S.wM = W.wM;
+    S.Mw.assign(nE, 0.0);
+    for (int j = 0; j < W.M.ncol; ++j) S.Mw[W.dims[1].to_s[j]] = W.Mw[j];
+    return S;
+}
+// e1ve0.cpp:55-106 compute_E1vE0c + :32-52 consolidate.  Entries come out sorted by (iE1, iE0); explicit zeros are kept
+// (whether ibmisc's spcopy drops them is not visible in tree: unpinned, and harmless -- they are zeros).
+static void compute_E1vE0c(std::vector<Weighted const *> const &XuE1s, std::vector<Weighted const *> const &XuE0s, long nE,
+                           std::vector<long> &rows, std::vector<long> &cols, std::vector<double> &vals)
+{
+    struct T3 { long r, c; double v; };
+    std::vector<T3> E1vE0c;
+    std::vector<double> sE1(nE, 0.0);
+    for (size_t i = 0; i < XuE1s.size(); ++i) {
+        if (XuE1s[i]->M.nrow != XuE0s[i]->M.nrow) fail("compute_E1vE0c: exchange grids differ");
+        SparsifiedX X1 = sparsify_XuE(*XuE1s[i], nE), X0 = sparsify_XuE(*XuE0s[i], nE);
+        std::vector<double> sXuE0 = invert1(X0.wM), sXuE1 = invert1(X1.wM);
+        Csc E1uX = transpose(X1.M);
+        Csc XvE1 = scale_rows(sXuE1, X1.M);
+        Csc XvE0 = scale_rows(sXuE0, X0.M);
+        Csc local = mul(E1uX, sub(XvE0, XvE1));
+        for (int j = 0; j < local.ncol; ++j)
+            for (int p = local.ptr[j]; p < local.ptr[j + 1]; ++p) E1vE0c.push_back(T3{local.row[p], j, local.val[p]});
+        for (long e = 0; e < nE; ++e) sE1[e] += X1.Mw[e];
+    }
+    for (double &x : sE1) x = 1. / x;
+    for (T3 &t : E1vE0c) t.v *= sE1[t.r];
+    std::stable_sort(E1vE0c.begin(), E1vE0c.end(), [](T3 const &a, T3 const &b) { return a.r != b.r ? a.r < b.r : a.c < b.c; });
+    rows.clear(); cols.clear(); vals.clear();
+    for (size_t i = 0; i < E1vE0c.size(); ++i) {
+        if (!rows.empty() && rows.back() == E1vE0c[i].r && cols.back() == E1vE0c[i].c) vals.back() += E1vE0c[i].v;
+        else { rows.push_back(E1vE0c[i].r); cols.push_back(E1vE0c[i].c); vals.push_back(E1vE0c[i].v); }
+    }
+}
+
 }   // namespace orc
 
 // =======================================================================================
@@ -865,6 +962,32 @@ int orc_multivec_to_dense(long n, const long *index, const double *weights, cons
         for (long i = 0; i < nE; ++i) if (std::isnan(d[i])) d[i] = fill;
     }
     return 0;
+    ORC_CATCH(-1)
+}
+
+int orc_vartrans(const double *O, long ncell, int nin, int nout, const int *colptr, const int *row, const double *val,
+                 const double *b, double *Z)
+{
+    ORC_TRY
+    vartrans(O, ncell, nin, nout, colptr, row, val, b, Z);
+    return 0;
+    ORC_CATCH(-1)
+}
+// Two calls: rows == NULL returns the entry count; then with buffers.
+long orc_e1ve0c(int nsheet, void **XuE1, void **XuE0, long nE, long *rows, long *cols, double *vals)
+{
+    ORC_TRY
+    std::vector<Weighted const *> a, b;
+    for (int i = 0; i < nsheet; ++i) { a.push_back((Weighted *)XuE1[i]); b.push_back((Weighted *)XuE0[i]); }
+    std::vector<long> r, c;
+    std::vector<double> v;
+    compute_E1vE0c(a, b, nE, r, c, v);
+    if (rows) {
+        std::copy(r.begin(), r.end(), rows);
+        std::copy(c.begin(), c.end(), cols);
+        std::copy(v.begin(), v.end(), vals);
+    }
+    return (long)r.size();
     ORC_CATCH(-1)
 }
 

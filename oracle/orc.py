@@ -42,6 +42,9 @@ def lib():
         L.orc_w_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orc_multivec_to_dense.argtypes = [C.c_long, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_long,
                                             C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_vartrans.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.orc_e1ve0c.restype = C.c_long
+        L.orc_e1ve0c.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_linterp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_nearest.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.orc_hntr_new.restype = C.c_void_p
@@ -149,6 +152,33 @@ class Gcm:
         if getattr(self, "_h", None):
             lib().orc_gcm_free(self._h)
             self._h = None
+
+
+def vartrans(O, M, b):
+    """Z = O * M + b (IceCoupler.cpp:203-252, :404-446).  O: [ncell, nin]; M: scipy sparse [nin, nout]; b: [nout]."""
+    import scipy.sparse
+    O = _c(np.atleast_2d(O), np.float64)
+    Mc = scipy.sparse.csc_matrix(M)
+    Mc.sort_indices()
+    assert Mc.shape[0] == O.shape[1]
+    cp = _c(Mc.indptr, np.int32); row = _c(Mc.indices, np.int32); val = _c(Mc.data, np.float64); b = _c(b, np.float64)
+    Z = np.zeros((O.shape[0], Mc.shape[1]))
+    if lib().orc_vartrans(_p(O), O.shape[0], O.shape[1], Mc.shape[1], _p(cp), _p(row), _p(val), _p(b), _p(Z)) != 0:
+        raise _err()
+    return Z
+
+
+def e1ve0c(XuE1s, XuE0s, nE):
+    """e1ve0.cpp:55-106.  XuE*: lists of oracle Weighted (XvE, scale=False, correctA=True, rows = all exchange cells).
+    Returns (iE1, iE0, val) sorted by (iE1, iE0), sparse E indices."""
+    n = len(XuE1s)
+    a = (C.c_void_p * n)(*[w._h for w in XuE1s]); b = (C.c_void_p * n)(*[w._h for w in XuE0s])
+    cnt = lib().orc_e1ve0c(n, a, b, nE, None, None, None)
+    if cnt < 0:
+        raise _err()
+    r = np.zeros(cnt, np.int64); c = np.zeros(cnt, np.int64); v = np.zeros(cnt)
+    lib().orc_e1ve0c(n, a, b, nE, _p(r), _p(c), _p(v))
+    return r, c, v
 
 
 def linterp(xp, xx):

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "icebin/coupler_b200.hpp"
 #include "icebin/regrid_b200.hpp"
 
 using namespace icebin;
@@ -92,6 +93,53 @@ int main(int argc, char **argv)
     threw = false;
     try { modele::Hntr bad(17.17, modele::HntrSpec(144, 90, 0., 2.0), g8); } catch (Exception const &) { threw = true; }
     CHECK(threw);
+
+    // coupling step, regridding side (IceCoupler.cpp:340-497, :203-252, e1ve0.cpp:55-106)
+    {
+        IceCouplerRegrid cpl(&gcm, 0, sheet.nX());
+        const int nv = 2;
+        std::vector<double> ice_ovalsI((size_t)nv * nI);
+        for (long i = 0; i < nI; ++i) { ice_ovalsI[i] = 1.0; ice_ovalsI[nI + i] = 0.5 * i; }
+        VarTransT id2 = VarTransT::identity(nv);
+        id2.b[0] = 2.0;                                               // first variable: x -> x + 2
+        VectorMultivec outA(nv), outE(nv);
+        auto step0 = cpl.couple_regrid(ice_ovalsI, nv, em, {&id2, &id2}, {&outA, &outE});
+        CHECK(outE.size() == (size_t)cpl.dimE()->dense_extent() && outA.size() > 0);
+        // E side is built without area correction: regridding the constant 1 (+2) gives weight * 3
+        for (size_t i = 0; i < outE.size(); ++i) CHECK(std::abs(outE.val(0, i) / outE.weights[i] - 3.0) < 1e-12);
+        std::vector<double> scaleE, dense;
+        outE.to_dense((long)gcm.nE(), -1.0, scaleE, dense);
+        long touched = 0;
+        for (unsigned long e = 0; e < gcm.nE(); ++e) { if (dense[e] != -1.0) { ++touched; CHECK(std::abs(dense[e] - 3.0) < 1e-12); } }
+        CHECK(touched == (long)outE.size());
+        // gcm -> ice with the IvE of that step (scale=t, correctA=t): a constant E field comes back as the constant times the
+        // native/projected area ratio of the GCM cell the ice cell lies in (M = diag(1/wM) IvEp diag(sEpvE))
+        const long nE0 = cpl.dimE()->dense_extent();
+        std::vector<double> gcm_ovalsE0((size_t)nv * nE0, 4.0);
+        auto ice_ivalsI = cpl.construct_ice_ivalsI(gcm_ovalsE0, id2);
+        for (long i = 0; i < nI; ++i) {
+            if (std::isnan(em[i])) continue;
+            const long ix = i / 6, iy = i % 6, iA = (iy / 2) * 4 + (ix / 2);
+            const double ratio = areaA[iA] / 4.0;
+            CHECK(std::abs(ice_ivalsI[i] / (6.0 * ratio) - 1) < 1e-12 && std::abs(ice_ivalsI[nI + i] / (4.0 * ratio) - 1) < 1e-12);
+        }
+        // second step with a thinner ice sheet: E1vE0c relates the two sets of elevation classes
+        std::vector<double> em1(em);
+        for (double &e : em1) if (!std::isnan(e)) e = 0.6 * e;
+        VectorMultivec outA1(nv), outE1(nv);
+        auto step1 = cpl.couple_regrid(ice_ovalsI, nv, em1, {&id2, &id2}, {&outA1, &outE1});
+        std::vector<std::unique_ptr<linear::Weighted>> X1, X0;
+        X1.push_back(std::move(step1.XuE));
+        X0.push_back(std::move(step0.XuE));
+        auto c10 = e1ve0::compute_E1vE0c(X1, X0, gcm.nE());
+        CHECK(!c10.empty());
+        bool nonzero = false;
+        for (size_t i = 1; i < c10.size(); ++i) CHECK(c10[i - 1].iE1 < c10[i].iE1 || (c10[i - 1].iE1 == c10[i].iE1 && c10[i - 1].iE0 < c10[i].iE0));
+        for (auto const &t : c10) nonzero = nonzero || t.value != 0.0;
+        CHECK(nonzero);
+        auto c11 = e1ve0::compute_E1vE0c(X1, X1, gcm.nE());
+        for (auto const &t : c11) CHECK(t.value == 0.0);
+    }
 
     std::printf("C++ API ok\n");
     return 0;
