@@ -88,6 +88,9 @@ class IceCouplerRegrid {
     std::unique_ptr<linear::Weighted> IvE0;
 public:
     struct CoupleOut {
+        // matrix_d() borrows its dims (RegridMatrices_Dynamic.cpp:412-423); the reference sparsifies XuE at once
+        // (GCMCoupler.cpp:500-505) -- here XuE travels with dims of its own, declared first so that they outlive it
+        std::unique_ptr<SparseSetT> dimX, dimE_XuE;
         std::unique_ptr<linear::Weighted> XuE;      // "XvE", scale=f, correctA=t: input of compute_E1vE0c
         SparseSetT const *dimE = nullptr;           // elevation classes in use after this step (owned by the coupler)
     };
@@ -155,9 +158,10 @@ public:
         }
         // IvE for interpreting the GCM's E-grid fields at the start of the next step (:470-472) and XuE (:474-477)
         auto IvE1 = rm->matrix_d("IvE", {&dimI, dimE1.get()}, RegridParams(true, true, sigma));
-        SparseSetT dimX = SparseSetT::identity(_nX);
         CoupleOut ret;
-        ret.XuE = rm->matrix_d("XvE", {&dimX, dimE1.get()}, RegridParams(false, true));
+        ret.dimX.reset(new SparseSetT(SparseSetT::identity(_nX)));
+        ret.dimE_XuE.reset(new SparseSetT((long)gcmr->nE(), dimE1->to_sparse()));       // same ids, same order as dimE1
+        ret.XuE = rm->matrix_d("XvE", {ret.dimX.get(), ret.dimE_XuE.get()}, RegridParams(false, true));
         dimE0 = std::move(dimE1);
         IvE0 = std::move(IvE1);
         ret.dimE = dimE0.get();

@@ -14,7 +14,9 @@ def build_exe():
     build.build()
     src = os.path.join(ROOT, "tests", "cpp", "test_api.cpp")
     so = os.path.join(ROOT, "icebin_b200", "libicebin_b200.so")
-    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(so)):
+    hdrs = [os.path.join(ROOT, "include", "icebin_b200.h")] + [os.path.join(ROOT, "include", "icebin", f)
+                                                             for f in os.listdir(os.path.join(ROOT, "include", "icebin"))]
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(f) for f in [src, so] + hdrs):
         subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
                                "-L", os.path.join(ROOT, "icebin_b200"), "-licebin_b200",
                                "-Wl,-rpath," + os.path.join(ROOT, "icebin_b200"), "-Wl,-rpath,/usr/local/cuda/lib64"])
