@@ -72,6 +72,13 @@ struct RegridMatrices {
     cudaStream_t stream = nullptr;
 };
 
+// balanced static partition of a plan's units over the CTAs of a launch configuration (apply.cu)
+struct BalanceTable {
+    int64_t nblk = 0;
+    int ntile = 0;
+    DBuf<int64_t> ranges;   // [nblk + 1]
+};
+
 // SpMM work decomposition (apply.cu): groups of short rows + chunks of long rows.  One apply at a time per matrix.
 struct ApplyPlan {
     bool ready = false;
@@ -91,6 +98,7 @@ struct ApplyPlan {
     DBuf<double> pv0, pv1;   // values of the column's first / second nonzero (0 if none)
     DBuf<int32_t> fx_ptr;    // [nrow+1] partial slots of each output row ...
     DBuf<uint32_t> fx_slot;  // ... in a fixed order
+    BalanceTable bal_rows, bal_pair;
     // distinct-column groups (matrices whose rows all have <= GC_S nonzeros, e.g. IvE, IvA): see gc_plan.cuh
     bool gc = false;
     int64_t gc_nitems = 0;
