@@ -894,6 +894,159 @@ __global__ void __launch_bounds__(GC_WARPS * 32) spmm_gc_kernel(const GcArgs a)
     }
 }
 
+// ---- per-warp streaming kernel for the pair plan (EvI) -------------------------------------------------------------
+// The CTA-wide ring of spmm_tma_kernel is consumer-bound: with fewer CTAs per SM it slows down in proportion (one CTA per
+// SM: 0.41 of peak), so its eight consumer warps, not HBM, set the pace.  Here every warp is its own pipeline, as in
+// spmm_gc_kernel: a warp owns one tile of 64*NQ fields and a CONTIGUOUS run of pair items (equal numbers of columns per
+// warp group, BalanceTable), walks the regrouped column stream record by record across item boundaries, and keeps a ring
+// of PW_R X-row pieces in flight: after a record is consumed its slot is refilled with the piece PW_R records ahead (one
+// bulk async copy issued by lane 0, completing on the slot's own mbarrier).  Column ids and the two values of a column
+// are staged through a small double-buffered shared-memory table, 32 records at a time, loaded one block ahead.  The
+// warps of a CTA work on the same items (one tile each), so the pieces of an X row are requested together.
+struct PwArgs {
+    const int4 *items;            // pair items (r0, begin, end, first partial slot)
+    const int64_t *ranges;        // [ngroup + 1] item ranges of the warp groups
+    int ngroup, ntile;
+    const int32_t *col;
+    const double *v0, *v1, *X;
+    int64_t ldx;
+    int nvar;
+    double *partials;
+    int64_t ldp;
+};
+constexpr int PW_B = 4;           // records per batch (one mbarrier round trip per batch)
+constexpr int PW_NB = 3;          // batches in the ring
+constexpr int PW_R = PW_B * PW_NB;
+constexpr int PW_WARPS = 4;       // warps per CTA
+
+template <int NQ>
+constexpr size_t pw_smem_bytes() { return (size_t)PW_WARPS * (PW_R * 64 * NQ * 8 + 2 * 32 * 24 + 64); }
+
+template <int NQ>
+__global__ void __launch_bounds__(PW_WARPS * 32) spmm_pw_kernel(const PwArgs a)
+{
+    constexpr int TW = 64 * NQ;
+    constexpr uint32_t ROWB = TW * 8;
+    constexpr uint32_t WARPB = PW_R * ROWB + 2 * 32 * 24 + 64;
+    extern __shared__ __align__(128) unsigned char pw_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *base = pw_raw + (size_t)warp * WARPB;
+    unsigned char *ring = base;
+    double *tv0 = reinterpret_cast<double *>(base + PW_R * ROWB);        // [2][32]
+    double *tv1 = tv0 + 64;                                              // [2][32]
+    int32_t *tcol = reinterpret_cast<int32_t *>(tv1 + 64);               // [2][32]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(base + PW_R * ROWB + 2 * 32 * 24);      // [PW_NB]
+    const unsigned FULL = 0xffffffffu;
+    if (lane < PW_NB) mbar_init(bar + lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const int64_t gw = (int64_t)blockIdx.x * PW_WARPS + warp;
+    const int group = (int)(gw / a.ntile), tile = (int)(gw % a.ntile);
+    if (group >= a.ngroup) return;
+    const int64_t ib = a.ranges[group], ie = a.ranges[group + 1];
+    if (ib >= ie) return;
+    const int f0 = tile * TW;
+    const uint32_t tb = (uint32_t)min(TW, a.nvar - f0) * 8u;
+    const int nq = min(NQ, (a.nvar - f0 + 63) >> 6);
+    const bool last_live = f0 + 64 * (nq - 1) + 2 * lane < a.nvar;
+    int4 it = __ldg(a.items + ib);
+    const int64_t P0 = it.y;
+    const int64_t n = __ldg(a.items + ie - 1).z - P0;                  // records of this warp
+    const int64_t nb = (n + PW_B - 1) / PW_B;
+    int4 it_next = ib + 1 < ie ? __ldg(a.items + ib + 1) : it;
+    int64_t item = ib;
+
+    // record blocks of 32: lane l holds record 32*j + l of block j
+    auto load_block = [&](int64_t j, int &c, double &x0, double &x1) {
+        const int64_t k = 32 * j + lane;
+        c = 0; x0 = 0.0; x1 = 0.0;
+        if (k < n) { c = __ldg(a.col + P0 + k); x0 = __ldg(a.v0 + P0 + k); x1 = __ldg(a.v1 + P0 + k); }
+    };
+    auto store_block = [&](int64_t j, int c, double x0, double x1) {
+        const int o = (int)(j & 1) * 32 + lane;
+        tcol[o] = c; tv0[o] = x0; tv1[o] = x1;
+    };
+    // X-row pieces of batch b -> ring batch b % PW_NB: lane r < PW_B fetches record PW_B*b + r
+    auto issue_batch = [&](int64_t b) {
+        const int bs = (int)(b % PW_NB);
+        const int64_t k = PW_B * b + lane;
+        const int cnt = (int)min((int64_t)PW_B, n - PW_B * b);
+        if (lane == 0) mbar_expect_tx(bar + bs, tb * (uint32_t)cnt);
+        __syncwarp();
+        if (lane < cnt) {
+            const int c = tcol[(int)((k >> 5) & 1) * 32 + (int)(k & 31)];
+            bulk_g2s(ring + (size_t)(bs * PW_B + lane) * ROWB, a.X + (int64_t)c * a.ldx + f0, tb, bar + bs);
+        }
+    };
+    int rc; double r0v, r1v;
+    load_block(0, rc, r0v, r1v);
+    store_block(0, rc, r0v, r1v);
+    load_block(1, rc, r0v, r1v);
+    __syncwarp();
+    for (int64_t b = 0; b < nb && b < PW_NB; ++b) issue_batch(b);
+    uint32_t phase = 0;
+    double2 acc0[NQ], acc1[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { acc0[q] = make_double2(0.0, 0.0); acc1[q] = make_double2(0.0, 0.0); }
+    const double2 *xb = reinterpret_cast<const double2 *>(ring) + lane;
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t k0 = PW_B * b;
+        if ((k0 & 31) == 0) {           // entering block j: publish block j+1 (its table half was block j-1's), load block j+2
+            const int64_t j = k0 >> 5;
+            __syncwarp();
+            store_block(j + 1, rc, r0v, r1v);
+            load_block(j + 2, rc, r0v, r1v);
+            __syncwarp();
+        }
+        const int bs = (int)(b % PW_NB);
+        mbar_wait(bar + bs, (phase >> bs) & 1u);
+        phase ^= 1u << bs;
+        // all table and ring reads of the batch first, then the arithmetic record by record
+        const int o = (int)((k0 >> 5) & 1) * 32 + (int)(k0 & 31);          // PW_B divides 32: a batch never straddles blocks
+        double v0[PW_B], v1[PW_B];
+        double2 x[PW_B][NQ];
+#pragma unroll
+        for (int r = 0; r < PW_B; ++r) {
+            v0[r] = tv0[o + r];
+            v1[r] = tv1[o + r];
+            const double2 *xr = xb + (bs * PW_B + r) * (TW / 2);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) x[r][q] = xr[q * 32];
+        }
+#pragma unroll
+        for (int r = 0; r < PW_B; ++r) {
+            if (k0 + r < n) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    acc0[q].x = acc0[q].x + v0[r] * x[r][q].x;
+                    acc0[q].y = acc0[q].y + v0[r] * x[r][q].y;
+                    acc1[q].x = acc1[q].x + v1[r] * x[r][q].x;
+                    acc1[q].y = acc1[q].y + v1[r] * x[r][q].y;
+                }
+                if (P0 + k0 + r + 1 == it.z) {      // item complete: its two partial rows (summed in a fixed order by the fix-up)
+                    double2 *p0 = reinterpret_cast<double2 *>(a.partials + (int64_t)it.w * a.ldp + f0) + lane;
+                    double2 *p1 = reinterpret_cast<double2 *>(a.partials + (int64_t)(it.w + 1) * a.ldp + f0) + lane;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        if (q < nq - 1 || (q == nq - 1 && last_live)) { p0[q * 32] = acc0[q]; p1[q * 32] = acc1[q]; }
+                        acc0[q] = make_double2(0.0, 0.0);
+                        acc1[q] = make_double2(0.0, 0.0);
+                    }
+                    ++item;
+                    it = it_next;
+                    if (item + 1 < ie) it_next = __ldg(a.items + item + 1);
+                }
+            }
+        }
+        // refill the ring batch with the pieces PW_NB batches ahead (the reads above are complete: their values were used)
+        if (b + PW_NB < nb) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            issue_batch(b + PW_NB);
+        }
+    }
+}
+
 // ---- plain-load fallback (small / odd nvar, unaligned buffers) ---------------------------------------------
 // A group of L lanes (power of two) owns one (item, field-tile) unit; lane fl owns VEC consecutive fields.
 template <int VEC>
@@ -1251,7 +1404,42 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
                 SpmmArgs a{P.pair_items.p, nun, ntile, tw, nstage, W.rowptr.p, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, dY, ldy, pp.p, ldp,
                            0, 0x7fffffff, 2, nullptr, W.nrow, P.fx_ptr.p, P.fx_slot.p};
                 static const bool skipfix = getenv("IB_SPMM_SKIPFIX") != nullptr;      // timing experiments only
-                if (!launch(spmm_tma_kernel<true>, occ1, a, nun, true, (int64_t)P.pcol.n, &P.bal_pair) && !skipfix) {
+                static const int pw = getenv("IB_SPMM_PW") ? atoi(getenv("IB_SPMM_PW")) : 0;       // per-warp streaming kernel
+                bool main_done = false;
+                if (pw > 0 && nvar >= 64) {
+                    static bool pw_attr = false;
+                    if (!pw_attr) {
+                        IB_CUDA(cudaFuncSetAttribute(spmm_pw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_smem_bytes<2>()));
+                        IB_CUDA(cudaFuncSetAttribute(spmm_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_smem_bytes<1>()));
+                        pw_attr = true;
+                    }
+                    const int nq = pw == 1 ? 1 : 2;
+                    const int ptile = (nvar + 64 * nq - 1) / (64 * nq);
+                    const size_t psmem = nq == 2 ? pw_smem_bytes<2>() : pw_smem_bytes<1>();
+                    auto pk = nq == 2 ? spmm_pw_kernel<2> : spmm_pw_kernel<1>;
+                    int pocc = 0;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, pk, PW_WARPS * 32, psmem);
+                    pocc = std::max(pocc, 1);
+                    const int64_t nwarps = (int64_t)sm_count() * pocc * PW_WARPS;
+                    const int64_t ngroup = std::max<int64_t>(1, std::min<int64_t>(P.pair_nitems, nwarps / ptile));
+                    BalanceTable &bt = P.bal_pw;
+                    if (bt.nblk != ngroup || bt.ntile != 1) {
+                        bt.ranges.alloc((size_t)ngroup + 1, s);
+                        unit_ranges_kernel<<<(unsigned)cdiv(ngroup + 1, 128), 128, 0, s>>>(P.pair_items.p, P.pair_nitems, 1, (int64_t)P.pcol.n, (int)ngroup, bt.ranges.p);
+                        IB_LAUNCHED();
+                        bt.nblk = ngroup; bt.ntile = 1;
+                    }
+                    PwArgs pa{P.pair_items.p, bt.ranges.p, (int)ngroup, ptile, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, pp.p, ldp};
+                    pk<<<(unsigned)cdiv(ngroup * ptile, PW_WARPS), PW_WARPS * 32, psmem, s>>>(pa);
+                    IB_LAUNCHED();
+                    main_done = true;
+                }
+                if (main_done) {
+                    if (!skipfix) {
+                        const int64_t tot = W.nrow * (int64_t)(nvar / 2);
+                        launch_dependent(spmm_fixup_list_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.fx_ptr.p, P.fx_slot.p, W.nrow, pp.p, ldp, nvar, dY, ldy);
+                    }
+                } else if (!launch(spmm_tma_kernel<true>, occ1, a, nun, true, (int64_t)P.pcol.n, &P.bal_pair) && !skipfix) {
                     const int64_t tot = W.nrow * (int64_t)(nvar / 2);
                     launch_dependent(spmm_fixup_list_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.fx_ptr.p, P.fx_slot.p, W.nrow, pp.p, ldp, nvar, dY, ldy);
                 }

@@ -98,7 +98,7 @@ struct ApplyPlan {
     DBuf<double> pv0, pv1;   // values of the column's first / second nonzero (0 if none)
     DBuf<int32_t> fx_ptr;    // [nrow+1] partial slots of each output row ...
     DBuf<uint32_t> fx_slot;  // ... in a fixed order
-    BalanceTable bal_rows, bal_pair;
+    BalanceTable bal_rows, bal_pair, bal_pw;
     // distinct-column groups (matrices whose rows all have <= GC_S nonzeros, e.g. IvE, IvA): see gc_plan.cuh
     bool gc = false;
     int64_t gc_nitems = 0;

@@ -95,6 +95,24 @@ def test_apply_distinct_column_groups_bitexact(cfg2, spec, nvar):
     assert np.array_equal(Yh[:, :nvar].T, Yref) and np.all(Yh[:, nvar:] == -7.0)
 
 
+@pytest.mark.parametrize("spec", ["EvI", "AvI"])
+@pytest.mark.parametrize("nvar", [64, 200, 512])
+def test_apply_wide_matrices_many_fields(cfg2, spec, nvar):
+    """EvI (pair-grouped column plan) and AvI (chunked long rows) with full and ragged field tiles against the oracle,
+    within 1e-12 of the sum of the magnitudes of a row's terms; deterministic from call to call."""
+    import scipy.sparse
+    go, gg = make_oracle(cfg2), make_gpu(cfg2)
+    em = cfg2["elevmask"][0]
+    Wo = go.matrix(0, em, spec, scale=True, correctA=True)
+    Wg = gg.regrid_matrices(cfg2["sheets"][0].name, em, scale=True, correctA=True).matrix(spec)
+    X = np.random.default_rng(nvar).uniform(-1, 1, (Wo.shape[1], nvar))
+    Yo = Wo.apply(np.ascontiguousarray(X.T)).T
+    Yg = Wg.apply(X, layout="cell")
+    A = scipy.sparse.csr_matrix((np.abs(Wo.val), (Wo.row, Wo.col)), shape=Wo.shape)
+    assert np.all(np.abs(Yg - Yo) <= 1e-12 * (A @ np.abs(X)) + 1e-300)
+    assert np.array_equal(Yg, Wg.apply(X, layout="cell"))
+
+
 def test_distinct_column_groups_graph_replay(cfg2):
     """The group kernel hands its units out through a device counter that is never reset (the last warp records where
     the next launch starts), so a captured apply can be replayed, mixed with eager applies and row blocks."""
