@@ -15,7 +15,7 @@ from ._lib import IceBinError, check, lib, vp
 
 __all__ = ["GCMRegridder", "RegridMatrices", "Weighted", "SparseSet", "HntrSpec", "Hntr", "IceBinError",
            "coo_matvec", "multivec_to_dense", "device_count", "launch_count", "apply_many", "apply_many_dev",
-           "vartrans_dev", "vartrans", "e1ve0c"]
+           "vartrans_dev", "vartrans", "e1ve0c", "exgrid_rectilinear"]
 
 
 def _p(a):
@@ -475,6 +475,22 @@ def e1ve0c(XuE1s, XuE0s, nE):
     r = np.zeros(cnt, np.int64); c = np.zeros(cnt, np.int64); v = np.zeros(cnt)
     check(min(lib().ib_e1ve0c(n, a, b, int(nE), _p(r), _p(c), _p(v)), 0))
     return r, c, v
+
+
+def exgrid_rectilinear(polys, iA, xe, ye, iI_major_x=True):
+    """Exchange grid of projected GCM polygons with a rectilinear ice grid (gridgen/GridGen_Exchange.cpp:175-316).
+    polys: list of [n_i, 2] vertex arrays in the ice grid's plane; iA: their GCM cell indices; xe, ye: ice cell edges.
+    Returns (ex_ij int32 [n, 2] = (iA, iI), ex_area [n]) -- the contents of an ExchangeGrid (AbbrGrid.hpp:40-78)."""
+    pptr = np.zeros(len(polys) + 1, np.int32)
+    np.cumsum([len(p) for p in polys], out=pptr[1:])
+    pxy = _c(np.concatenate([np.asarray(p, np.float64).reshape(-1, 2) for p in polys]) if len(polys) else np.zeros((0, 2)), np.float64)
+    iA = _c(iA, np.int64); xe = _c(xe, np.float64); ye = _c(ye, np.float64)
+    args = (len(polys), _p(pptr), _p(pxy), _p(iA), len(xe) - 1, _p(xe), len(ye) - 1, _p(ye), int(iI_major_x))
+    n = lib().ib_exgrid_rectilinear(*args, None, None)
+    check(min(n, 0))
+    ij = np.zeros((n, 2), np.int32); area = np.zeros(n)
+    check(min(lib().ib_exgrid_rectilinear(*args, _p(ij), _p(area)), 0))
+    return ij, area
 
 
 def multivec_to_dense(index, weights, vals, nE, fill=np.nan):

@@ -21,6 +21,7 @@ UNITS = {
     "apply.cu": ["-fmad=false"],
     "smooth.cu": ["-fmad=false"],
     "couple.cu": ["-fmad=false"],
+    "exgrid.cu": ["-fmad=false"],
     "hntr.cu": [],
     "merge.cu": [],
     "capi.cu": [],

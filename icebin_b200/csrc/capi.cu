@@ -65,6 +65,10 @@ void vartrans_dev(const double *, int64_t, int64_t, int, int, const int32_t *, c
 void e1ve0c(int, Weighted *const *, Weighted *const *, int64_t, std::vector<int64_t> &, std::vector<int64_t> &, std::vector<double> &,
             cudaStream_t);
 
+// exgrid.cu
+int64_t exgrid_rectilinear(int, const int32_t *, const double *, const int64_t *, int, const double *, int, const double *, int, int32_t *,
+                           double *, cudaStream_t);
+
 // merge.cu
 void merge_pack(const double *, int64_t, int, const int32_t *, int64_t, double *, cudaStream_t);
 void merge_unpack(double *, int64_t, int, int64_t, const int32_t *, const double *, const double *, const double *, cudaStream_t);
@@ -756,6 +760,14 @@ int64_t ib_e1ve0c(int32_t nsheet, const ib_weighted *const *XuE1, const ib_weigh
     std::copy(c.begin(), c.end(), cols);
     std::copy(v.begin(), v.end(), vals);
     return (int64_t)r.size();
+    IB_CATCH
+}
+
+int64_t ib_exgrid_rectilinear(int32_t npoly, const int32_t *pptr, const double *pxy, const int64_t *iA, int32_t nx, const double *xe,
+                              int32_t ny, const double *ye, int iI_major_x, int32_t *ex_ij, double *ex_area)
+{
+    IB_TRY
+    return exgrid_rectilinear(npoly, pptr, pxy, iA, nx, xe, ny, ye, iI_major_x, ex_ij, ex_area, default_stream());
     IB_CATCH
 }
 

@@ -190,6 +190,18 @@ int ib_vartrans_dev(const double *dO, int64_t ldo, int64_t ncell, int32_t nin, i
 int64_t ib_e1ve0c(int32_t nsheet, const ib_weighted *const *XuE1, const ib_weighted *const *XuE0, int64_t nE, int64_t *rows,
                   int64_t *cols, double *vals);
 
+/* ---- Exchange-grid generation for a rectilinear ice grid (the step in front of the path: SURVEY 8f rank 4) --- */
+/* make_exchange_grid(gridA, gridI, sproj)   gridgen/GridGen_Exchange.cpp:208-316 (+ overlap_callback :175-204), for GCM
+ * cells given as polygons ALREADY PROJECTED into the ice grid's plane (pptr[npoly+1] vertex ranges into pxy[nv][2];
+ * the reference subdivides the sides of lon-lat cells before projecting, so 4..92 vertices, not necessarily convex) and
+ * an ice grid of rectangles with edges xe[nx+1], ye[ny+1].  Every (polygon, ice cell) overlap of positive area becomes
+ * an exchange cell (iA[p], iI, area): Sutherland-Hodgman clipping + shoelace area instead of CGAL + Cell::proj_area.
+ * iI = ix*ny + iy if iI_major_x (PISM order, gridgen/searise_grid.cpp:104-108) else iy*nx + ix.
+ * Order: polygons in input order, ice cells ascending inside one.  Call with ex_ij == NULL for the count (the result is
+ * kept on this thread), then with ex_ij[2*n] (interleaved iA, iI: ExchangeGrid::indices) and ex_area[n]. */
+int64_t ib_exgrid_rectilinear(int32_t npoly, const int32_t *pptr, const double *pxy, const int64_t *iA, int32_t nx,
+                              const double *xe, int32_t ny, const double *ye, int iI_major_x, int32_t *ex_ij, double *ex_area);
+
 /* ---- Hntr ------------------------------------------------------------------------------------------ */
 /* Hntr(yp17, Bspec, Aspec, DATMIS); HntrSpec(im, jm, offi, dlat[minutes])   hntr.cpp:63-82, GridSpec.hpp:143-170 */
 int ib_hntr_create(ib_hntr **out, int imB, int jmB, double offiB, double dlatB, int imA, int jmA, double offiA,

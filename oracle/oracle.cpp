@@ -843,6 +843,68 @@ static void compute_E1vE0c(std::vector<Weighted const *> const &XuE1s, std::vect
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Exchange grid of projected GCM polygons with a rectilinear ice grid.
+// gridgen/GridGen_Exchange.cpp:175-316: for every GCM cell, the ice cells under its bounding box (RTree search), the
+// overlap polygon (CGAL there; here a rectangle window, so Sutherland-Hodgman clipping against its four sides is exact
+// up to rounding) and its area by the shoelace formula (Cell::proj_area).  CGAL is not in this image: parity unpinned.
+typedef std::vector<std::pair<double, double>> Poly;
+static Poly clip_halfplane(Poly const &in, int axis, bool keep_ge, double c)
+{
+    Poly out;
+    for (size_t i = 0; i < in.size(); ++i) {
+        auto const &p = in[i];
+        auto const &q = in[(i + 1) % in.size()];
+        const double pv = axis == 0 ? p.first : p.second, qv = axis == 0 ? q.first : q.second;
+        const bool pin = keep_ge ? pv >= c : pv <= c, qin = keep_ge ? qv >= c : qv <= c;
+        if (pin) out.push_back(p);
+        if (pin != qin) {
+            const double t = (c - pv) / (qv - pv);
+            if (axis == 0) out.push_back({c, p.second + t * (q.second - p.second)});
+            else out.push_back({p.first + t * (q.first - p.first), c});
+        }
+    }
+    return out;
+}
+static double poly_area(Poly const &v)
+{
+    double s = 0.0;
+    for (size_t i = 0; i < v.size(); ++i) {
+        auto const &p = v[i];
+        auto const &q = v[(i + 1) % v.size()];
+        s += p.first * q.second - q.first * p.second;
+    }
+    s *= 0.5;
+    return s < 0 ? -s : s;
+}
+static void exgrid_rect(int npoly, const int *pptr, const double *pxy, const long *iA, int nx, const double *xe, int ny,
+                        const double *ye, bool major_x, std::vector<int> &ij, std::vector<double> &area)
+{
+    ij.clear(); area.clear();
+    for (int p = 0; p < npoly; ++p) {
+        Poly poly;
+        for (int v = pptr[p]; v < pptr[p + 1]; ++v) poly.push_back({pxy[2 * v], pxy[2 * v + 1]});
+        double x0 = poly[0].first, x1 = x0, y0 = poly[0].second, y1 = y0;
+        for (auto const &v : poly) { x0 = std::min(x0, v.first); x1 = std::max(x1, v.first); y0 = std::min(y0, v.second); y1 = std::max(y1, v.second); }
+        std::vector<std::pair<long, double>> cells;      // (iI, area)
+        for (int ix = 0; ix < nx; ++ix) {
+            if (xe[ix + 1] <= x0 || xe[ix] >= x1) continue;
+            for (int iy = 0; iy < ny; ++iy) {
+                if (ye[iy + 1] <= y0 || ye[iy] >= y1) continue;
+                Poly c = clip_halfplane(poly, 0, true, xe[ix]);
+                if (c.size() >= 3) c = clip_halfplane(c, 0, false, xe[ix + 1]);
+                if (c.size() >= 3) c = clip_halfplane(c, 1, true, ye[iy]);
+                if (c.size() >= 3) c = clip_halfplane(c, 1, false, ye[iy + 1]);
+                if (c.size() < 3) continue;
+                const double a = poly_area(c);
+                if (a > 0) cells.push_back({major_x ? (long)ix * ny + iy : (long)iy * nx + ix, a});
+            }
+        }
+        std::sort(cells.begin(), cells.end());
+        for (auto const &c : cells) { ij.push_back((int)iA[p]); ij.push_back((int)c.first); area.push_back(c.second); }
+    }
+}
+
 }   // namespace orc
 
 // =======================================================================================
@@ -988,6 +1050,19 @@ long orc_e1ve0c(int nsheet, void **XuE1, void **XuE0, long nE, long *rows, long 
         std::copy(v.begin(), v.end(), vals);
     }
     return (long)r.size();
+    ORC_CATCH(-1)
+}
+
+// Two calls: ex_ij == NULL returns the count.
+long orc_exgrid(int npoly, const int *pptr, const double *pxy, const long *iA, int nx, const double *xe, int ny, const double *ye,
+                int major_x, int *ex_ij, double *ex_area)
+{
+    ORC_TRY
+    std::vector<int> ij;
+    std::vector<double> area;
+    exgrid_rect(npoly, pptr, pxy, iA, nx, xe, ny, ye, major_x != 0, ij, area);
+    if (ex_ij) { std::copy(ij.begin(), ij.end(), ex_ij); std::copy(area.begin(), area.end(), ex_area); }
+    return (long)area.size();
     ORC_CATCH(-1)
 }
 

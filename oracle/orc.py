@@ -45,6 +45,9 @@ def lib():
         L.orc_vartrans.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.orc_e1ve0c.restype = C.c_long
         L.orc_e1ve0c.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_exgrid.restype = C.c_long
+        L.orc_exgrid.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_void_p]
         L.orc_linterp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_nearest.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.orc_hntr_new.restype = C.c_void_p
@@ -179,6 +182,21 @@ def e1ve0c(XuE1s, XuE0s, nE):
     r = np.zeros(cnt, np.int64); c = np.zeros(cnt, np.int64); v = np.zeros(cnt)
     lib().orc_e1ve0c(n, a, b, nE, _p(r), _p(c), _p(v))
     return r, c, v
+
+
+def exgrid_rectilinear(polys, iA, xe, ye, iI_major_x=True):
+    """gridgen/GridGen_Exchange.cpp:175-316 for projected GCM polygons x a rectilinear ice grid.  Returns (ex_ij [n,2], ex_area [n])."""
+    pptr = np.zeros(len(polys) + 1, np.int32)
+    np.cumsum([len(p) for p in polys], out=pptr[1:])
+    pxy = _c(np.concatenate([np.asarray(p, np.float64).reshape(-1, 2) for p in polys]), np.float64)
+    iA = _c(iA, np.int64); xe = _c(xe, np.float64); ye = _c(ye, np.float64)
+    args = (len(polys), _p(pptr), _p(pxy), _p(iA), len(xe) - 1, _p(xe), len(ye) - 1, _p(ye), int(iI_major_x))
+    n = lib().orc_exgrid(*args, None, None)
+    if n < 0:
+        raise _err()
+    ij = np.zeros((n, 2), np.int32); area = np.zeros(n)
+    lib().orc_exgrid(*args, _p(ij), _p(area))
+    return ij, area
 
 
 def linterp(xp, xx):
