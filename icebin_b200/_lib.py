@@ -26,6 +26,8 @@ SIGNATURES = {
     "ib_gcm_create": (C.c_int, [PP, i64, i32, vp, vp, i32, vp, C.c_int]),
     "ib_gcm_free": (None, [vp]),
     "ib_gcm_add_sheet": (C.c_int, [vp, cp, i64, i32, vp, vp, vp, i64, vp, vp, vp, C.c_int]),
+    "ib_gcm_filter_cellsA": (C.c_int, [vp, vp]),
+    "ib_gcm_nA_realized": (i64, [vp]),
     "ib_gcm_nA": (i64, [vp]),
     "ib_gcm_nE": (i64, [vp]),
     "ib_gcm_nhc": (i32, [vp]),

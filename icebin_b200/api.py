@@ -288,6 +288,20 @@ class GCMRegridder:
     def nI(self, sheet_name):
         return int(lib().ib_gcm_nI(self._h, self.sheets[sheet_name]))
 
+    def nX(self, sheet_name):
+        return int(lib().ib_gcm_nX(self._h, self.sheets[sheet_name]))
+
+    def filter_cellsA(self, keepA):
+        """GCMRegridder_Standard::filter_cellsA(keepA) (GCMRegridder.hpp:380-389): restrict every sheet's exchange grid and
+        the GCM grid's realised set to the kept GCM cells (a rank's / a GPU's domain).  keepA: bool [nA] or a predicate on iA."""
+        if callable(keepA):
+            keepA = np.array([bool(keepA(i)) for i in range(self.nA)])
+        k = _c(np.asarray(keepA) != 0, np.uint8)
+        if k.shape != (self.nA,):
+            raise ValueError("keepA must have nA=%d elements" % self.nA)
+        check(lib().ib_gcm_filter_cellsA(self._h, _p(k)))
+        self._n_real = int(lib().ib_gcm_nA_realized(self._h))
+
     def add_sheet(self, name, sheet, interp_style="Z_INTERP"):
         dimI = _c(sheet.dimI, np.int64)
         areaI = _c(sheet.native_areaI, np.float64)

@@ -318,6 +318,72 @@ __global__ void scale_vals_kernel(const int32_t *row, const int32_t *col, const 
     val[j] = v;
 }
 
+// ---- filter_cellsA: domain restriction of the exchange grids (GCMRegridder.cpp:154-164) ---------------------------
+struct KeepLoad {
+    const int2 *ex_ij;
+    const uint8_t *keepA;
+    __device__ uint32_t operator()(int64_t x) const { return keepA[ex_ij[x].x] ? 1u : 0u; }
+};
+struct KeepScatter {
+    const int2 *ex_ij;
+    const double *ex_area;
+    int2 *out_ij;
+    double *out_area;
+    __device__ void operator()(int64_t x, uint32_t prefix, uint32_t keep) const
+    {
+        if (keep) { out_ij[prefix] = ex_ij[x]; out_area[prefix] = ex_area[x]; }
+    }
+};
+
+// IceRegridder::filter_cellsA (IceRegridder.cpp:150-178) -> ExchangeGrid::filter_cellsB (AbbrGrid.cpp:33-49): keep the
+// exchange cells whose GCM cell is kept, in their original order; the survivors are renumbered (the comment at
+// IceRegridder.cpp:170-176 explains why that is harmless).  Upstream applies the predicate to the exchange cell's own id
+// (IceRegridder.cpp:163) and reads the ids from the still-empty output vector (AbbrGrid.cpp:39); what is implemented here is
+// the documented intent (GCMRegridder.hpp:380-389: "remove cells that do not interact with the cells we've kept").
+void filter_cellsA(Gcm &g, const uint8_t *keepA_h, cudaStream_t s)
+{
+    ensure_device();
+    DBuf<uint8_t> keep((size_t)g.nA, s);
+    keep.upload(keepA_h, (size_t)g.nA);
+    for (auto &shp : g.sheets) {
+        Sheet &sh = *shp;
+        int64_t nkeep = 0;
+        if (sh.nX > 0) {
+            ScanState<uint32_t> st;
+            KeepLoad L{sh.ex_ij.p, keep.p};
+            transform_scan<uint32_t>(st, sh.nX, L, AddU32{}, 0u, s);
+            uint32_t tot = 0;
+            IB_CUDA(cudaMemcpyAsync(&tot, st.total.p, sizeof tot, cudaMemcpyDeviceToHost, s));
+            IB_CUDA(cudaStreamSynchronize(s));
+            nkeep = tot;
+            DBuf<int2> nij((size_t)nkeep, s);
+            DBuf<double> narea((size_t)nkeep, s);
+            scan_apply<uint32_t>(st, L, AddU32{}, 0u, KeepScatter{sh.ex_ij.p, sh.ex_area.p, nij.p, narea.p}, s);
+            IB_CUDA(cudaStreamSynchronize(s));
+            sh.ex_ij = std::move(nij);
+            sh.ex_area = std::move(narea);
+        }
+        sh.nX = nkeep;
+        // agridA->filter_cells(keepA): the sheet's per-realised-A-cell data follow the GCM grid's realised set
+        std::vector<double> proj;
+        for (size_t d = 0; d < g.dimA_h.size(); ++d)
+            if (keepA_h[g.dimA_h[d]]) proj.push_back(sh.gridA_proj_area_h[d]);
+        sh.gridA_proj_area_h.swap(proj);
+        std::vector<double> ratio((size_t)g.nA, 0.0);
+        size_t k = 0;
+        for (size_t d = 0; d < g.dimA_h.size(); ++d)
+            if (keepA_h[g.dimA_h[d]]) { ratio[(size_t)g.dimA_h[d]] = g.native_area_h[d] / sh.gridA_proj_area_h[k]; ++k; }
+        sh.ratioA.upload(ratio.data(), (size_t)g.nA);
+        IB_CUDA(cudaStreamSynchronize(s));
+    }
+    std::vector<int64_t> dimA;
+    std::vector<double> area;
+    for (size_t d = 0; d < g.dimA_h.size(); ++d)
+        if (keepA_h[g.dimA_h[d]]) { dimA.push_back(g.dimA_h[d]); area.push_back(g.native_area_h[d]); }
+    g.dimA_h.swap(dimA);
+    g.native_area_h.swap(area);
+}
+
 struct SpecPlan {
     int kindB, kindA, form, useE, needPos;
     int combiner;   // 0 AEvI, 1 IvAE, 2 EvA

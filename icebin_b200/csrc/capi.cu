@@ -224,6 +224,15 @@ int ib_gcm_create(ib_gcm **out, int64_t nA, int32_t n_real, const int64_t *dimA,
 }
 void ib_gcm_free(ib_gcm *g) { delete g; }
 
+int ib_gcm_filter_cellsA(ib_gcm *G, const uint8_t *keepA)
+{
+    IB_TRY
+    if (!G || !keepA) fail(IB_ERR_ARG, "ib_gcm_filter_cellsA: bad argument");
+    filter_cellsA(G->g, keepA, default_stream());
+    return IB_OK;
+    IB_CATCH
+}
+
 int ib_gcm_add_sheet(ib_gcm *G, const char *name, int64_t nI, int32_t n_real_I, const int64_t *dimI, const double *native_areaI,
                      const double *centroid_xy, int64_t nX, const int32_t *ex_ij, const double *ex_area,
                      const double *gridA_proj_area, int interp_style)
@@ -267,6 +276,7 @@ int ib_gcm_add_sheet(ib_gcm *G, const char *name, int64_t nI, int32_t n_real_I, 
     IB_CATCH
 }
 
+int64_t ib_gcm_nA_realized(const ib_gcm *G) { return G ? (int64_t)G->g.dimA_h.size() : -1; }
 int64_t ib_gcm_nA(const ib_gcm *G) { return G->g.nA; }
 int64_t ib_gcm_nE(const ib_gcm *G) { return G->g.nE(); }
 int32_t ib_gcm_nhc(const ib_gcm *G) { return (int32_t)G->g.hcdefs_h.size(); }

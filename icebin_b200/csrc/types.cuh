@@ -125,6 +125,8 @@ struct Weighted {
 
 std::unique_ptr<Weighted> build_matrix(RegridMatrices &rm, std::string const &spec, Dim *d0, Dim *d1,
                                        Params const &p, bool own_dims);
+// build.cu: GCMRegridder_Standard::filter_cellsA (GCMRegridder.cpp:154-164)
+void filter_cellsA(Gcm &g, const uint8_t *keepA, cudaStream_t s);
 // smooth.cu: M <- smoothI * M  (RegridMatrices_Dynamic.cpp:236-248)
 void smooth_rows(RegridMatrices &rm, Weighted &W, Params const &p);
 // apply.cu

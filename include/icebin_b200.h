@@ -82,6 +82,13 @@ int64_t ib_gcm_nX(const ib_gcm *, int sheet);      /* IceRegridder.hpp nX() */
 int ib_gcm_nsheets(const ib_gcm *);
 int ib_gcm_sheet_index(const ib_gcm *, const char *name);   /* ice_regridders().index.at(name) */
 int ib_gcm_correctA(const ib_gcm *);
+/* GCMRegridder_Standard::filter_cellsA(keepA)  GCMRegridder.hpp:380-389, GCMRegridder.cpp:154-164 (domain decomposition:
+ * every MPI rank / GPU keeps its own GCM cells).  keepA[nA]: nonzero = keep.  Exchange cells of dropped GCM cells are
+ * removed from every sheet (the survivors keep their order and are renumbered, IceRegridder.cpp:170-176) and the GCM
+ * grid's realised set shrinks.  Matrices already built are unaffected; regrid_matrices() built afterwards see the
+ * restricted grids. */
+int ib_gcm_filter_cellsA(ib_gcm *, const uint8_t *keepA);
+int64_t ib_gcm_nA_realized(const ib_gcm *);        /* agridA.dim.dense_extent() */
 /* GCMRegridder::wA(accum, sheet, native)  GCMRegridder.hpp:304-314: index[n_real], area[n_real] */
 int ib_gcm_wA(const ib_gcm *, int sheet, int native, int64_t *index, double *area);
 

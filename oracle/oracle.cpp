@@ -1066,6 +1066,34 @@ long orc_exgrid(int npoly, const int *pptr, const double *pxy, const long *iA, i
     ORC_CATCH(-1)
 }
 
+// GCMRegridder_Standard::filter_cellsA(keepA) (GCMRegridder.cpp:154-164) with the documented intent of
+// IceRegridder::filter_cellsA / ExchangeGrid::filter_cellsB (IceRegridder.cpp:150-178, AbbrGrid.cpp:33-49): exchange
+// cells of dropped GCM cells go (order kept), then agridA->filter_cells(keepA).  keep[nA], nonzero = keep.
+int orc_filter_cellsA(void *g_, const unsigned char *keep)
+{
+    ORC_TRY
+    Gcm *g = (Gcm *)g_;
+    for (auto &sp : g->sheets) {
+        Sheet &s = *sp;
+        std::vector<int> ij;
+        std::vector<double> ar;
+        for (long x = 0; x < s.nX; ++x)
+            if (keep[s.ex_ij[2 * x]]) { ij.push_back(s.ex_ij[2 * x]); ij.push_back(s.ex_ij[2 * x + 1]); ar.push_back(s.ex_area[x]); }
+        s.ex_ij.swap(ij); s.ex_area.swap(ar);
+        s.nX = (long)s.ex_area.size();
+        std::vector<double> proj;
+        for (size_t d = 0; d < g->A.dim.size(); ++d) if (keep[g->A.dim[d]]) proj.push_back(s.gridA_proj_area[d]);
+        s.gridA_proj_area.swap(proj);
+    }
+    std::vector<long> dim;
+    std::vector<double> area;
+    for (size_t d = 0; d < g->A.dim.size(); ++d) if (keep[g->A.dim[d]]) { dim.push_back(g->A.dim[d]); area.push_back(g->A.native_area[d]); }
+    g->A.dim.swap(dim); g->A.native_area.swap(area);
+    return 0;
+    ORC_CATCH(-1)
+}
+long orc_nX(void *g_, int sheet) { return ((Gcm *)g_)->sheets[sheet]->nX; }
+
 int orc_linterp(const double *xp, int n, double xx, long *idx, double *w)
 {
     ORC_TRY

@@ -48,6 +48,9 @@ def lib():
         L.orc_exgrid.restype = C.c_long
         L.orc_exgrid.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                  C.c_void_p, C.c_void_p]
+        L.orc_filter_cellsA.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_nX.restype = C.c_long
+        L.orc_nX.argtypes = [C.c_void_p, C.c_int]
         L.orc_linterp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_nearest.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.orc_hntr_new.restype = C.c_void_p
@@ -136,6 +139,15 @@ class Gcm:
         if r < 0:
             raise _err()
         return r
+
+    def filter_cellsA(self, keepA):
+        """GCMRegridder_Standard::filter_cellsA (GCMRegridder.cpp:154-164).  keepA: bool [nA]."""
+        k = _c(np.asarray(keepA) != 0, np.uint8)
+        if lib().orc_filter_cellsA(self._h, _p(k)) != 0:
+            raise _err()
+
+    def nX(self, sheet):
+        return int(lib().orc_nX(self._h, sheet))
 
     def matrix(self, sheet, elevmaskI, spec, scale=True, correctA=False, sigma=(0., 0., 0.), dims=(None, None)):
         em = _c(elevmaskI, np.float64)
