@@ -35,6 +35,27 @@ def plan_shared(local_ids, n_sparse, group=None):
     return shared_ids, loc, slot_of_row
 
 
+def partition_cellsA(ex_iA, nA, world):
+    """Domain decomposition of ONE sheet's build over `world` ranks by GCM cells (the reference shards global_ec by ranges of
+    coarse-grid cells and concatenates, modele/global_ec.cpp:818-893): GCM cells in ascending index order are cut into
+    `world` contiguous runs holding (nearly) equal numbers of exchange cells.  Returns keep[world, nA] bool masks for
+    GCMRegridder.filter_cellsA; every (A, I) and (E, I) matrix row then lives on exactly one rank, so AvI / EvI of the ranks
+    concatenate, while I-side matrices of ice cells that straddle a cut are summed (unscaled) across the two ranks."""
+    ex_iA = np.asarray(ex_iA, dtype=np.int64)
+    cnt = np.bincount(ex_iA, minlength=nA)
+    used = np.nonzero(cnt)[0]
+    cum = np.cumsum(cnt[used])
+    total = int(cum[-1]) if len(cum) else 0
+    keep = np.zeros((world, nA), bool)
+    lo = 0
+    for r in range(world):
+        hi = int(np.searchsorted(cum, total * (r + 1) / world, side="left")) + 1 if r + 1 < world else len(used)
+        hi = max(hi, lo)
+        keep[r, used[lo:hi]] = True
+        lo = hi
+    return keep
+
+
 def merge_reference(contribs, n_sparse, fill=np.nan):
     """Numpy statement of the merge for tests: contribs = [(ids, wM, num[nrow, nvar]), ...] -> dense [n_sparse, nvar]."""
     nvar = contribs[0][2].shape[1]

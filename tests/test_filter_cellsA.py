@@ -73,3 +73,53 @@ def test_gpu_filter_cellsA_parity(which, request):
     g2 = make_gpu(cfg)
     g2.filter_cellsA(lambda iA: bool(keep[iA]))
     assert g2.nX(name) == go.nX(0)
+
+
+def test_partition_cellsA_is_a_balanced_partition(cfg2):
+    from icebin_b200 import multi
+    sh, nA = cfg2["sheets"][0], cfg2["gridA"].nA
+    used = np.unique(sh.ex_ij[:, 0])
+    for world in (1, 2, 3, 8):
+        keep = multi.partition_cellsA(sh.ex_ij[:, 0], nA, world)
+        assert keep.shape == (world, nA) and np.array_equal(keep.sum(0) > 0, np.isin(np.arange(nA), used))
+        assert keep.sum(0).max() == 1                                   # every used GCM cell on exactly one rank
+        load = np.array([keep[r][sh.ex_ij[:, 0]].sum() for r in range(world)])
+        assert load.sum() == sh.nX and load.max() <= sh.nX / world + np.bincount(sh.ex_ij[:, 0]).max()
+        for r in range(world):                                          # contiguous runs of GCM cells
+            ids = np.nonzero(keep[r])[0]
+            if len(ids):
+                assert np.array_equal(ids, used[(used >= ids[0]) & (used <= ids[-1])])
+
+
+@pytest.mark.gpu
+def test_gpu_sharded_build_concatenates_to_the_full_matrices(cfg2):
+    """One sheet's build cut over 4 domains by GCM-cell ranges (each domain is what one GPU would hold): the AvI / EvI rows
+    of the domains are disjoint and, put together, are the full matrices bit for bit; the unscaled IvA add up."""
+    from icebin_b200 import multi
+    sh, em, nA = cfg2["sheets"][0], cfg2["elevmask"][0], cfg2["gridA"].nA
+    full = make_gpu(cfg2).regrid_matrices(sh.name, em, scale=True, correctA=True)
+    keep = multi.partition_cellsA(sh.ex_ij[:, 0], nA, 4)
+
+    def sparse(W):
+        r, c, v = W.to_coo_dense()
+        return sp.csr_matrix((v, (W.dim(0)[r], W.dim(1)[c])), shape=W.sparse_extent)
+    parts = []
+    for r in range(4):
+        g = make_gpu(cfg2)
+        g.filter_cellsA(keep[r])
+        parts.append(g.regrid_matrices(sh.name, em, scale=True, correctA=True))
+    for spec in ("AvI", "EvI"):
+        F = sparse(full.matrix(spec))
+        S = sum(sparse(p.matrix(spec)) for p in parts)
+        assert (F != S).nnz == 0, spec
+        rows = [np.unique(p.matrix(spec).dim(0)) for p in parts]
+        assert sum(len(x) for x in rows) == len(np.unique(np.concatenate(rows)))        # disjoint row sets
+    fu = make_gpu(cfg2).regrid_matrices(sh.name, em, scale=False, correctA=False)
+    F = sparse(fu.matrix("IvA"))
+    S = None
+    for r in range(4):
+        g = make_gpu(cfg2)
+        g.filter_cellsA(keep[r])
+        M = sparse(g.regrid_matrices(sh.name, em, scale=False, correctA=False).matrix("IvA"))
+        S = M if S is None else S + M
+    assert abs(F - S).max() <= 1e-12 * abs(F).max()
