@@ -68,6 +68,7 @@ SIGNATURES = {
     "ib_multivec_to_dense": (C.c_int, [i64, vp, vp, vp, i32, i64, f64, vp, vp]),
     "ib_vartrans_dev": (C.c_int, [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
     "ib_e1ve0c": (i64, [i32, vp, vp, i64, vp, vp, vp]),
+    "ib_w_combine_chunks": (C.c_int, [i32, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "ib_exgrid_rectilinear": (i64, [i32, vp, vp, vp, i32, vp, i32, vp, C.c_int, vp, vp]),
     "ib_merge_pack_dev": (C.c_int, [vp, i64, i32, vp, i64, vp, vp]),
     "ib_merge_unpack_dev": (C.c_int, [vp, i64, i32, i64, vp, vp, vp, vp, vp]),

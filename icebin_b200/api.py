@@ -15,7 +15,7 @@ from ._lib import IceBinError, check, lib, vp
 
 __all__ = ["GCMRegridder", "RegridMatrices", "Weighted", "SparseSet", "HntrSpec", "Hntr", "IceBinError",
            "coo_matvec", "multivec_to_dense", "device_count", "launch_count", "apply_many", "apply_many_dev",
-           "vartrans_dev", "vartrans", "e1ve0c", "exgrid_rectilinear"]
+           "vartrans_dev", "vartrans", "e1ve0c", "exgrid_rectilinear", "combine_chunks"]
 
 
 def _p(a):
@@ -489,6 +489,20 @@ def e1ve0c(XuE1s, XuE0s, nE):
     r = np.zeros(cnt, np.int64); c = np.zeros(cnt, np.int64); v = np.zeros(cnt)
     check(min(lib().ib_e1ve0c(n, a, b, int(nE), _p(r), _p(c), _p(v)), 0))
     return r, c, v
+
+
+def combine_chunks(chunks, scale=True):
+    """combine_chunks (modele/combine_global_ec.cpp:95-262): concatenate per-chunk UNSCALED matrices into one matrix in sparse
+    indexing, scaled by 1 / (sum of wM over all chunks) per row.  Returns (M: scipy coo [sparse extents] with the entries in
+    chunk order, duplicates NOT merged; (wM_index, wM_val); (Mw_index, Mw_val))."""
+    import scipy.sparse
+    n = len(chunks)
+    Wp = (vp * n)(*[w._h for w in chunks])
+    nnz = sum(w.nnz for w in chunks); nr = sum(w.shape[0] for w in chunks); nc = sum(w.shape[1] for w in chunks)
+    r = np.zeros(nnz, np.int64); c = np.zeros(nnz, np.int64); v = np.zeros(nnz)
+    wi = np.zeros(nr, np.int64); wv = np.zeros(nr); mi = np.zeros(nc, np.int64); mv = np.zeros(nc)
+    check(lib().ib_w_combine_chunks(n, Wp, int(scale), _p(r), _p(c), _p(v), _p(wi), _p(wv), _p(mi), _p(mv)))
+    return scipy.sparse.coo_matrix((v, (r, c)), shape=chunks[0].sparse_extent), (wi, wv), (mi, mv)
 
 
 def exgrid_rectilinear(polys, iA, xe, ye, iI_major_x=True):

@@ -65,6 +65,8 @@ void vartrans_dev(const double *, int64_t, int64_t, int, int, const int32_t *, c
 void e1ve0c(int, Weighted *const *, Weighted *const *, int64_t, std::vector<int64_t> &, std::vector<int64_t> &, std::vector<double> &,
             cudaStream_t);
 
+void combine_chunks(int, Weighted *const *, bool, int64_t *, int64_t *, double *, int64_t *, double *, int64_t *, double *, cudaStream_t);
+
 // exgrid.cu
 int64_t exgrid_rectilinear(int, const int32_t *, const double *, const int64_t *, int, const double *, int, const double *, int, int32_t *,
                            double *, cudaStream_t);
@@ -770,6 +772,22 @@ int64_t ib_e1ve0c(int32_t nsheet, const ib_weighted *const *XuE1, const ib_weigh
     std::copy(c.begin(), c.end(), cols);
     std::copy(v.begin(), v.end(), vals);
     return (int64_t)r.size();
+    IB_CATCH
+}
+
+int ib_w_combine_chunks(int32_t nchunk, const ib_weighted *const *W, int scale, int64_t *M_row, int64_t *M_col, double *M_val,
+                        int64_t *wM_index, double *wM_val, int64_t *Mw_index, double *Mw_val)
+{
+    IB_TRY
+    if (nchunk <= 0 || !W || !M_row || !M_col || !M_val || !wM_index || !wM_val || !Mw_index || !Mw_val)
+        fail(IB_ERR_ARG, "ib_w_combine_chunks: bad argument");
+    std::vector<Weighted *> w((size_t)nchunk);
+    for (int i = 0; i < nchunk; ++i) {
+        if (!W[i]) fail(IB_ERR_ARG, "ib_w_combine_chunks: null chunk");
+        w[i] = W[i]->w.get();
+    }
+    combine_chunks(nchunk, w.data(), scale != 0, M_row, M_col, M_val, wM_index, wM_val, Mw_index, Mw_val, default_stream());
+    return IB_OK;
     IB_CATCH
 }
 

@@ -3,6 +3,8 @@
 //   vartrans_dev       Z = O * M + b          unit/variable conversion in front of a regrid apply
 //                                             (IceCoupler.cpp:203-252 gcm -> ice, :404-446 ice -> gcm)
 //   e1ve0c             E1vE0c = sE1 * sum_sheets E1uX * (XvE0 - XvE1)   (e1ve0.cpp:55-106, GCMCoupler.cpp:488-515)
+//   combine_chunks     per-chunk unscaled matrices -> one matrix in sparse indexing, scaled by 1/sum_chunks wM
+//                                             (modele/combine_global_ec.cpp:95-262)
 //
 // Compiled with -fmad=false; additions run in the reference's order wherever that order is defined.
 #include <algorithm>
@@ -237,6 +239,83 @@ void e1ve0c(int nsheet, Weighted *const *XuE1, Weighted *const *XuE0, int64_t nE
     dcol.download(cols.data(), (size_t)n2);
     out.download(vals.data(), (size_t)n2);
     IB_CUDA(cudaStreamSynchronize(s));
+}
+
+// ---- combine_chunks (modele/combine_global_ec.cpp:95-262) ----------------------------------------------------------
+// The reference computes global matrices in chunks (ranges of GCM cells, modele/global_ec.cpp:818-893; here also one chunk
+// per ice sheet or per GPU domain) and concatenates them: every chunk's entries are relabelled with SPARSE indices,
+// weights wM are accumulated per sparse row over all chunks first (sM_s = 1 / sum wM), and with `scale` every entry is
+// multiplied by sM_s of its row.  Entries and weights are concatenated in chunk order, not merged (:233 checks the count).
+__global__ void expand_rows_kernel(const int32_t *rowptr, int64_t nrow, int32_t *row);      // apply.cu
+__global__ void cc_entries_kernel(const int32_t *row, const int32_t *col, const double *val, int64_t nnz, const int64_t *sp0,
+                                  const int64_t *sp1, const double *sM, int scale, int64_t *orow, int64_t *ocol, double *oval)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nnz) return;
+    const int64_t rs = e1_sparse(sp0, row[j]);
+    orow[j] = rs;
+    ocol[j] = e1_sparse(sp1, col[j]);
+    oval[j] = scale ? val[j] * (1. / sM[rs]) : val[j];
+}
+__global__ void cc_ids_kernel(const int64_t *sp, int64_t n, int64_t *out)
+{
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n) out[d] = e1_sparse(sp, (int32_t)d);
+}
+
+void combine_chunks(int nchunk, Weighted *const *W, bool scale, int64_t *M_row, int64_t *M_col, double *M_val, int64_t *wM_index,
+                    double *wM_val, int64_t *Mw_index, double *Mw_val, cudaStream_t s)
+{
+    ensure_device();
+    if (nchunk <= 0) fail(IB_ERR_ARG, "combine_chunks: no chunks");
+    for (int i = 0; i < nchunk; ++i) {
+        if (!W[i]->dims[0] || !W[i]->dims[1]) fail(IB_ERR_ARG, "combine_chunks: chunk %d has no dims", i);
+        if (W[i]->scaled) fail(IB_ERR_ARG, "combine_chunks: chunk %d is scaled; chunks must be built with scale = false (global_ec.cpp:273)", i);
+        for (int k = 0; k < 2; ++k)
+            if (W[i]->dims[k]->sparse_extent != W[0]->dims[k]->sparse_extent)
+                fail(IB_ERR_DIM, "combine_chunks: chunk %d lives in a different sparse space", i);
+    }
+    const int64_t n0 = W[0]->dims[0]->sparse_extent;
+    if (n0 <= 0) fail(IB_ERR_ARG, "combine_chunks: unknown sparse extent");
+    DBuf<double> sM((size_t)n0, s);
+    sM.zero();
+    for (int i = 0; i < nchunk; ++i) {       // weights first, chunk after chunk (combine_global_ec.cpp:157-174)
+        Weighted &w = *W[i];
+        if (w.nrow > 0) {
+            e1_scatter_add_kernel<<<(unsigned)cdiv(w.nrow, 256), 256, 0, s>>>(w.wM.p, w.dims[0]->identity ? nullptr : w.dims[0]->sparse_of.p, w.nrow, sM.p);
+            IB_LAUNCHED();
+        }
+    }
+    int64_t o_nnz = 0, o_row = 0, o_col = 0;
+    for (int i = 0; i < nchunk; ++i) {
+        Weighted &w = *W[i];
+        const int64_t *sp0 = w.dims[0]->identity ? nullptr : w.dims[0]->sparse_of.p;
+        const int64_t *sp1 = w.dims[1]->identity ? nullptr : w.dims[1]->sparse_of.p;
+        if (w.nnz > 0) {
+            DBuf<int32_t> row((size_t)w.nnz, s);
+            DBuf<int64_t> dr((size_t)w.nnz, s), dc((size_t)w.nnz, s);
+            DBuf<double> dv((size_t)w.nnz, s);
+            expand_rows_kernel<<<(unsigned)cdiv(w.nrow, 128), 128, 0, s>>>(w.rowptr.p, w.nrow, row.p);
+            IB_LAUNCHED();
+            cc_entries_kernel<<<(unsigned)cdiv(w.nnz, 256), 256, 0, s>>>(row.p, w.col.p, w.val.p, w.nnz, sp0, sp1, sM.p, scale ? 1 : 0, dr.p, dc.p, dv.p);
+            IB_LAUNCHED();
+            dr.download(M_row + o_nnz, (size_t)w.nnz);
+            dc.download(M_col + o_nnz, (size_t)w.nnz);
+            dv.download(M_val + o_nnz, (size_t)w.nnz);
+            IB_CUDA(cudaStreamSynchronize(s));
+        }
+        for (int k = 0; k < 2; ++k) {
+            const int64_t n = k == 0 ? w.nrow : w.ncol;
+            if (n == 0) continue;
+            DBuf<int64_t> ids((size_t)n, s);
+            cc_ids_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(k == 0 ? sp0 : sp1, n, ids.p);
+            IB_LAUNCHED();
+            ids.download(k == 0 ? wM_index + o_row : Mw_index + o_col, (size_t)n);
+            (k == 0 ? w.wM : w.Mw).download(k == 0 ? wM_val + o_row : Mw_val + o_col, (size_t)n);
+            IB_CUDA(cudaStreamSynchronize(s));
+        }
+        o_nnz += w.nnz; o_row += w.nrow; o_col += w.ncol;
+    }
 }
 
 }   // namespace ib

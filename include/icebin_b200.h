@@ -197,6 +197,14 @@ int ib_vartrans_dev(const double *dO, int64_t ldo, int64_t ncell, int32_t nin, i
 int64_t ib_e1ve0c(int32_t nsheet, const ib_weighted *const *XuE1, const ib_weighted *const *XuE0, int64_t nE, int64_t *rows,
                   int64_t *cols, double *vals);
 
+/* combine_chunks(ifnames, ofname, sgrids, scale)   modele/combine_global_ec.cpp:95-262: the reference computes global
+ * matrices in chunks (ranges of GCM cells, one file each) and concatenates them; here a chunk is an UNSCALED ib_weighted
+ * (one per GCM-cell domain, GPU or ice sheet).  Entries are relabelled with sparse indices and, if `scale`, multiplied by
+ * 1 / (sum over all chunks of wM) of their row; wM and Mw are returned as sparse (index, value) lists.  Everything is
+ * concatenated in chunk order, nothing is merged.  Buffer sizes: sum of nnz, of nrow and of ncol over the chunks (ib_w_info). */
+int ib_w_combine_chunks(int32_t nchunk, const ib_weighted *const *W, int scale, int64_t *M_row, int64_t *M_col, double *M_val,
+                        int64_t *wM_index, double *wM_val, int64_t *Mw_index, double *Mw_val);
+
 /* ---- Exchange-grid generation for a rectilinear ice grid (the step in front of the path: SURVEY 8f rank 4) --- */
 /* make_exchange_grid(gridA, gridI, sproj)   gridgen/GridGen_Exchange.cpp:208-316 (+ overlap_callback :175-204), for GCM
  * cells given as polygons ALREADY PROJECTED into the ice grid's plane (pptr[npoly+1] vertex ranges into pxy[nv][2];

@@ -1094,6 +1094,35 @@ int orc_filter_cellsA(void *g_, const unsigned char *keep)
 }
 long orc_nX(void *g_, int sheet) { return ((Gcm *)g_)->sheets[sheet]->nX; }
 
+// combine_chunks (modele/combine_global_ec.cpp:95-262): per-chunk unscaled matrices -> one matrix in sparse indexing.
+// Buffers: M_* [sum nnz], wM_* [sum nrow], Mw_* [sum ncol].  Entries of a chunk in its COO (column-major) order.
+int orc_combine_chunks(int nchunk, void **W_, int scale, long *M_row, long *M_col, double *M_val, long *wM_index, double *wM_val,
+                       long *Mw_index, double *Mw_val)
+{
+    ORC_TRY
+    std::vector<Weighted *> W;
+    for (int i = 0; i < nchunk; ++i) W.push_back((Weighted *)W_[i]);
+    const long shape0 = W[0]->dims[0].sparse_extent;
+    std::vector<double> sM_s(shape0, 0.0);
+    for (Weighted *w : W)
+        for (int i = 0; i < w->M.nrow; ++i) sM_s[w->dims[0].to_s[i]] += w->wM[i];
+    for (double &x : sM_s) x = 1. / x;
+    long on = 0, orow = 0, ocol = 0;
+    for (Weighted *w : W) {
+        for (int i = 0; i < w->M.nrow; ++i) { wM_index[orow] = w->dims[0].to_s[i]; wM_val[orow] = w->wM[i]; ++orow; }
+        for (int j = 0; j < w->M.ncol; ++j)
+            for (int p = w->M.ptr[j]; p < w->M.ptr[j + 1]; ++p) {
+                const long iB_s = w->dims[0].to_s[w->M.row[p]], iA_s = w->dims[1].to_s[j];
+                M_row[on] = iB_s; M_col[on] = iA_s;
+                M_val[on] = scale ? w->M.val[p] * sM_s[iB_s] : w->M.val[p];
+                ++on;
+            }
+        for (int j = 0; j < w->M.ncol; ++j) { Mw_index[ocol] = w->dims[1].to_s[j]; Mw_val[ocol] = w->Mw[j]; ++ocol; }
+    }
+    return 0;
+    ORC_CATCH(-1)
+}
+
 int orc_linterp(const double *xp, int n, double xx, long *idx, double *w)
 {
     ORC_TRY

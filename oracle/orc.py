@@ -51,6 +51,7 @@ def lib():
         L.orc_filter_cellsA.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_nX.restype = C.c_long
         L.orc_nX.argtypes = [C.c_void_p, C.c_int]
+        L.orc_combine_chunks.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7
         L.orc_linterp.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_nearest.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.orc_hntr_new.restype = C.c_void_p
@@ -209,6 +210,19 @@ def exgrid_rectilinear(polys, iA, xe, ye, iI_major_x=True):
     ij = np.zeros((n, 2), np.int32); area = np.zeros(n)
     lib().orc_exgrid(*args, _p(ij), _p(area))
     return ij, area
+
+
+def combine_chunks(chunks, scale=True):
+    """modele/combine_global_ec.cpp:95-262.  chunks: oracle Weighted built with scale=False.  Returns (coo M, (wM idx, val), (Mw idx, val))."""
+    import scipy.sparse
+    n = len(chunks)
+    a = (C.c_void_p * n)(*[w._h for w in chunks])
+    nnz = sum(w.nnz for w in chunks); nr = sum(w.shape[0] for w in chunks); nc = sum(w.shape[1] for w in chunks)
+    r = np.zeros(nnz, np.int64); c = np.zeros(nnz, np.int64); v = np.zeros(nnz)
+    wi = np.zeros(nr, np.int64); wv = np.zeros(nr); mi = np.zeros(nc, np.int64); mv = np.zeros(nc)
+    if lib().orc_combine_chunks(n, a, int(scale), _p(r), _p(c), _p(v), _p(wi), _p(wv), _p(mi), _p(mv)) != 0:
+        raise _err()
+    return scipy.sparse.coo_matrix((v, (r, c)), shape=chunks[0].sparse_extent), (wi, wv), (mi, mv)
 
 
 def linterp(xp, xx):
