@@ -358,6 +358,35 @@ def run_b200(args):
     kms = [a.elapsed_time(b) for a, b in kev]
     evi_ms = statistics.mean(kms)
 
+    # ---- the I-side applies of the same matrix set (north star: "batched AvI/EvI/IvE application"), each alone, CUDA
+    # events around a loop of applies; reported beside the headline, not part of it
+    other = None
+    if world == 1 and not args.no_e2e:
+        try:
+            other = {}
+            peak_o, _ = measured_peak()
+            YI = torch.empty((nI_d, nvar), dtype=torch.float64, device=dev)
+            for name, Xin in (("IvE", YE), ("IvA", YA)):
+                M = mats[name]
+                assert M.shape == (nI_d, Xin.shape[0])
+                for _ in range(3):
+                    M.apply_dev(Xin.data_ptr(), nvar, nvar, YI.data_ptr(), nvar, True, stream)
+                oe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                nrep = max(3, min(args.steps, 100))
+                oe[0].record()
+                for _ in range(nrep):
+                    M.apply_dev(Xin.data_ptr(), nvar, nvar, YI.data_ptr(), nvar, True, stream)
+                oe[1].record()
+                torch.cuda.synchronize()
+                oms = oe[0].elapsed_time(oe[1]) / nrep
+                oalg = 12 * M.nnz + 4 * (M.shape[0] + 1) + 8 * nvar * (M.shape[0] + M.shape[1])
+                other[name] = {"shape": list(M.shape), "nnz": M.nnz, "ms": oms, "Gnnz_s": M.nnz * nvar / oms / 1e6,
+                               "alg_GBs": oalg / oms / 1e6, "frac_of_peak": oalg / oms / 1e6 / peak_o}
+            del YI
+        except Exception as e:      # never let the side measurement break the contract line
+            sys.stderr.write("bench.py: I-side applies not measured (%s)\n" % str(e).splitlines()[0])
+            other = None
+
     # ---- e2e: the reference-facing host-buffer call (ib_w_apply), H2D of X and D2H of Y inside the timed region
     e2e = None
     if world == 1 and not args.no_e2e:
@@ -416,6 +445,8 @@ def run_b200(args):
     line.update(line_extra)
     if e2e is not None:
         line["e2e"] = e2e
+    if other:
+        line["other_applies"] = other
     if world == 1 and not args.no_cpu_baseline:
         _, oE, oA, bs = cpu_reference_setup(cfg)
         nf = 64
