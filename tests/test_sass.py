@@ -1,0 +1,63 @@
+"""The built library contains what DESIGN.md says it does: sm_100a code only, 1-D bulk async copies (UBLKCP) completing on
+mbarriers (SYNCS) in the SpMM kernels that claim them, and fp64 arithmetic without fused multiply-add in the units compiled
+with -fmad=false (the bit-exactness argument rests on that).  Needs cuobjdump (CUDA toolkit), no GPU."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+def sass_by_function(obj):
+    out = subprocess.run([CUOBJDUMP, "-sass", obj], capture_output=True, text=True, check=True).stdout
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            funcs[cur] = []
+        elif cur is not None:
+            funcs[cur].append(line)
+    return out, {k: "\n".join(v) for k, v in funcs.items()}
+
+
+@pytest.fixture(scope="module")
+def apply_sass():
+    if not os.path.exists(CUOBJDUMP):
+        pytest.skip("cuobjdump not available")
+    from icebin_b200 import build
+    build.build()
+    obj = os.path.join(ROOT, "icebin_b200", "build", "apply.o")
+    if not os.path.exists(obj):
+        pytest.skip("object files not kept")
+    return sass_by_function(obj)
+
+
+def test_only_sm100a_code(apply_sass):
+    out, _ = apply_sass
+    archs = set(re.findall(r"arch = (sm_\w+)", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.parametrize("kernel", ["spmm_gc_kernel", "spmm_tma_kernel", "spmm_pw_kernel"])
+def test_bulk_async_copies_and_mbarriers(apply_sass, kernel):
+    _, funcs = apply_sass
+    mine = {k: v for k, v in funcs.items() if kernel in k}
+    assert mine, kernel
+    for name, body in mine.items():
+        assert "UBLKCP" in body, name + ": no bulk async copy (cp.async.bulk)"
+        assert "SYNCS" in body, name + ": no mbarrier operations"
+
+
+def test_no_fused_multiply_add_in_the_spmm_kernels(apply_sass):
+    """Rows are accumulated as acc = acc + v*x with separate roundings (Eigen's order on the CPU): no DFMA."""
+    _, funcs = apply_sass
+    for name, body in funcs.items():
+        if "spmm" in name:
+            assert "DFMA" not in body, name
+            if "fixup" not in name:
+                assert "DMUL" in body and "DADD" in body, name
