@@ -56,6 +56,17 @@ def test_no_cpu_fallback():
     with pytest.raises(api.IceBinError) as e:
         h.regrid(None, np.zeros(288 * 180))
     assert e.value.code == -2
+    # the entry points either side of the path (exchange-grid generation, variable transformation, device buffers)
+    import scipy.sparse
+    from icebin_b200._lib import lib, vp
+    with pytest.raises(api.IceBinError) as e:
+        api.exgrid_rectilinear([np.array([[0., 0.], [1., 0.], [1., 1.]])], [0], np.arange(3.), np.arange(3.))
+    assert e.value.code == -2
+    with pytest.raises(api.IceBinError) as e:
+        api.vartrans_dev(0x1000, 2, 1, scipy.sparse.identity(2, format="csc"), np.zeros(2), 0x2000, 2)
+    assert e.value.code == -2
+    p = vp()
+    assert lib().ib_dev_alloc(C.byref(p), 64) == -2 and not p.value
 
 
 def test_product_does_not_import_oracle():
