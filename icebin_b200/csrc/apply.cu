@@ -936,7 +936,6 @@ __global__ void __launch_bounds__(PW_WARPS * 32) spmm_pw_kernel(const PwArgs a)
     double *tv1 = tv0 + 64;                                              // [2][32]
     int32_t *tcol = reinterpret_cast<int32_t *>(tv1 + 64);               // [2][32]
     uint64_t *bar = reinterpret_cast<uint64_t *>(base + PW_R * ROWB + 2 * 32 * 24);      // [PW_NB]
-    const unsigned FULL = 0xffffffffu;
     if (lane < PW_NB) mbar_init(bar + lane, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
@@ -1402,7 +1401,7 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
                 const int64_t nun = P.pair_nitems * ntile;
                 DBuf<double> pp((size_t)(2 * P.pair_nitems) * ldp, s);
                 SpmmArgs a{P.pair_items.p, nun, ntile, tw, nstage, W.rowptr.p, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, dY, ldy, pp.p, ldp,
-                           0, 0x7fffffff, 2, nullptr, W.nrow, P.fx_ptr.p, P.fx_slot.p};
+                           0, 0x7fffffff, 2, nullptr, W.nrow, P.fx_ptr.p, P.fx_slot.p, nullptr};
                 static const bool skipfix = getenv("IB_SPMM_SKIPFIX") != nullptr;      // timing experiments only
                 static const int pw = getenv("IB_SPMM_PW") ? atoi(getenv("IB_SPMM_PW")) : 0;       // per-warp streaming kernel
                 bool main_done = false;
@@ -1446,7 +1445,7 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
                 pair_done = true;
             } else {
                 SpmmArgs a{P.items.p, nunits, ntile, tw, nstage, W.rowptr.p, W.col.p, W.val.p, nullptr, dX, ldx, nvar, dY, ldy, partials.p, ldp,
-                           rlo, rhi, 1, P.split_rows.p, P.nsplit_rows, nullptr, nullptr};
+                           rlo, rhi, 1, P.split_rows.p, P.nsplit_rows, nullptr, nullptr, nullptr};
                 // equal-size chunks: the strided deal is already even (and measured 3 % faster than contiguous runs on AvI)
                 static const bool balance_rows = getenv("IB_SPMM_BALANCE_ROWS") != nullptr;
                 if (launch(spmm_tma_kernel<false>, occ0, a, nunits, P.nsplit_rows > 0, W.nnz, balance_rows ? &P.bal_rows : nullptr)) pair_done = true;   // fix-up already done
