@@ -15,6 +15,7 @@
 #include <array>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -182,6 +183,16 @@ public:
         sheets_index[s.name] = ix;
         return ix;
     }
+    /** filter_cellsA(keepA) (GCMRegridder.hpp:380-389, GCMRegridder.cpp:154-164): keep only the GCM cells of this rank's /
+        GPU's domain; the exchange grids of all sheets are compacted on the device */
+    void filter_cellsA(std::function<bool(long)> const &keepA)
+    {
+        std::vector<uint8_t> keep((size_t)nA());
+        for (size_t i = 0; i < keep.size(); ++i) keep[i] = keepA((long)i) ? 1 : 0;
+        ib_check(ib_gcm_filter_cellsA(h, keep.data()));
+        n_real = (size_t)ib_gcm_nA_realized(h);
+    }
+    long nX(int sheet_index) const { return (long)ib_gcm_nX(h, sheet_index); }
     unsigned long nA() const { return (unsigned long)ib_gcm_nA(h); }
     unsigned long nE() const { return (unsigned long)ib_gcm_nE(h); }
     unsigned int nhc() const { return (unsigned int)ib_gcm_nhc(h); }
@@ -202,6 +213,41 @@ public:
         return std::unique_ptr<RegridMatrices_Dynamic>(new RegridMatrices_Dynamic(r, params));
     }
 };
+
+/** What combine_chunks() of modele/combine_global_ec.cpp:95-262 accumulates into its Weighted_Compressed: the chunks'
+    entries relabelled with sparse indices (scaled by 1 / sum of wM over the chunks if `scale`), and wM / Mw as sparse lists */
+struct CombinedChunks {
+    std::vector<int64_t> M_row, M_col, wM_index, Mw_index;
+    std::vector<double> M_val, wM_val, Mw_val;
+};
+inline CombinedChunks combine_chunks(std::vector<linear::Weighted const *> const &chunks, bool scale)
+{
+    CombinedChunks c;
+    size_t nnz = 0, nr = 0, nc = 0;
+    std::vector<const ib_weighted *> w;
+    for (auto *ch : chunks) { nnz += (size_t)ch->nnz(); nr += (size_t)ch->shape()[0]; nc += (size_t)ch->shape()[1]; w.push_back(ch->handle()); }
+    c.M_row.resize(nnz); c.M_col.resize(nnz); c.M_val.resize(nnz);
+    c.wM_index.resize(nr); c.wM_val.resize(nr); c.Mw_index.resize(nc); c.Mw_val.resize(nc);
+    ib_check(ib_w_combine_chunks((int32_t)w.size(), w.data(), scale, c.M_row.data(), c.M_col.data(), c.M_val.data(), c.wM_index.data(),
+                                 c.wM_val.data(), c.Mw_index.data(), c.Mw_val.data()));
+    return c;
+}
+
+/** make_exchange_grid (gridgen/GridGen_Exchange.cpp:208-316) for GCM cells given as polygons projected into the plane of a
+    rectilinear ice grid: fills ExchangeGrid::indices (interleaved iA, iI) and ::overlaps (AbbrGrid.hpp:40-78) */
+inline void make_exchange_grid_rectilinear(std::vector<int32_t> const &pptr, std::vector<double> const &pxy, std::vector<int64_t> const &iA,
+                                           std::vector<double> const &xe, std::vector<double> const &ye, bool iI_major_x,
+                                           std::vector<int32_t> &indices, std::vector<double> &overlaps)
+{
+    const int32_t npoly = (int32_t)iA.size();
+    int64_t n = ib_exgrid_rectilinear(npoly, pptr.data(), pxy.data(), iA.data(), (int32_t)xe.size() - 1, xe.data(), (int32_t)ye.size() - 1,
+                                      ye.data(), iI_major_x, nullptr, nullptr);
+    ib_check(n);
+    indices.resize((size_t)(2 * n)); overlaps.resize((size_t)n);
+    if (n > 0)
+        ib_check(ib_exgrid_rectilinear(npoly, pptr.data(), pxy.data(), iA.data(), (int32_t)xe.size() - 1, xe.data(), (int32_t)ye.size() - 1,
+                                       ye.data(), iI_major_x, indices.data(), overlaps.data()));
+}
 
 namespace modele {
 
