@@ -19,6 +19,8 @@ SIGNATURES = {
     "ib_device_count": (C.c_int, []),
     "ib_set_device": (C.c_int, [C.c_int]),
     "ib_launch_count": (i64, []),
+    "ib_tune": (C.c_int, [cp, C.c_int]),
+    "ib_trim": (C.c_int, []),
     "ib_dev_alloc": (C.c_int, [PP, i64]),
     "ib_dev_free": (None, [vp]),
     "ib_dev_upload": (C.c_int, [vp, vp, i64]),

@@ -30,6 +30,16 @@ def device_count():
     return lib().ib_device_count()
 
 
+def tune(key, value):
+    """Performance knobs of the library (ib_tune); results never depend on them."""
+    check(lib().ib_tune(key.encode(), int(value)))
+
+
+def trim():
+    """Give cached device memory back to the driver (ib_trim)."""
+    check(lib().ib_trim())
+
+
 def launch_count():
     return int(lib().ib_launch_count())
 

@@ -19,6 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 UNITS = {
     "build.cu": ["-fmad=false"],
     "apply.cu": ["-fmad=false"],
+    "apply_stream.cu": ["-fmad=false"],
     "smooth.cu": ["-fmad=false"],
     "couple.cu": ["-fmad=false"],
     "exgrid.cu": ["-fmad=false"],

@@ -21,13 +21,13 @@
 // oracle bit for bit; split rows differ only in association.
 //
 // Roofline: HBM.  Algorithmic bytes = 12*nnz + 4*(nrow+1) + 8*nvar*(ncol_touched + nrow)   (SURVEY 8d).
-#include <cooperative_groups.h>
-
-#include <cstdlib>
+#include <algorithm>
+#include <mutex>
 
 #include "gc_plan.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "tma.cuh"
 #include "types.cuh"
 #include "util.cuh"
 
@@ -35,7 +35,6 @@ namespace ib {
 
 constexpr int APPLY_CHUNK = 32;
 constexpr int GROUP_ROWS = 32;
-static int pair_chunk() { static int v = getenv("IB_PAIR_CHUNK") ? atoi(getenv("IB_PAIR_CHUNK")) : 48; return v; }
 
 // ---- plan -----------------------------------------------------------------------------------------------
 // item = (first_row, nnz_begin, nnz_end, w):  w >= 0: chunk of a long row, w = partial slot
@@ -82,7 +81,6 @@ struct PlanApply {
     }
 };
 
-static bool make_pair_plan(Weighted &W, cudaStream_t s);
 static void make_gc_plan(Weighted &W, cudaStream_t s);
 struct MaxU32 {
     __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
@@ -117,8 +115,7 @@ static void make_plan(Weighted &W, cudaStream_t s)
             IB_CUDA(cudaStreamSynchronize(s));
             P.max_row_len = (int)mx;
         }
-        make_pair_plan(W, s);
-        if (P.max_row_len <= GC_S && P.nsplit_rows == 0 && !getenv("IB_SPMM_NOGC")) make_gc_plan(W, s);
+        if (P.max_row_len <= GC_S && P.nsplit_rows == 0 && g_tune.use_gc) make_gc_plan(W, s);
     }
     P.ready = true;
 }
@@ -171,12 +168,6 @@ static void make_gc_plan(Weighted &W, cudaStream_t s)
     P.gc = true;
 }
 
-// ---- pair-grouped column plan ------------------------------------------------------------------------------
-// EvI-like matrices have (at most) two nonzeros per COLUMN: an ice cell feeds the two elevation classes that bracket
-// its elevation (IceRegridder_L0.cpp:126-143).  Row-wise processing then reads every X row twice.  Instead, columns
-// are regrouped by the pair of rows (r0, r1) they feed; a chunk of <= APPLY_CHUNK such columns is one item that reads
-// each X row ONCE and accumulates two partial rows (weights v0 -> r0, v1 -> r1).  Every output row is then the sum,
-// in a fixed order, of the partial rows listed for it (fx_ptr/fx_slot).
 __global__ void expand_rows_kernel(const int32_t *rowptr, int64_t nrow, int32_t *row)
 {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,233 +179,18 @@ __global__ void u32_to_i32_copy_kernel(const uint32_t *a, int64_t n, int32_t *b)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) b[i] = (int32_t)a[i];
 }
-// A column with n nonzeros becomes ceil(n/2) "virtual columns", each owning two consecutive nonzeros of the column
-// (ice cells on the border between GCM cells feed 4 or 8 elevation classes).  vcount -> scan -> vbase.
-struct VCountLoad {
-    const int32_t *colptr;
-    __device__ uint32_t operator()(int64_t c) const { return (uint32_t)((colptr[c + 1] - colptr[c] + 1) / 2); }
-};
-// per virtual column: key = (r0 << 32 | r1 + 1), owning column, first CSC entry
-struct VEmit {
-    const int32_t *colptr;
-    const uint32_t *perm;
-    const int32_t *row;
-    uint64_t *key;
-    uint32_t *vid, *vcol, *vent;
-    __device__ void operator()(int64_t c, uint32_t base, uint32_t nv) const
-    {
-        const int b = colptr[c], e = colptr[c + 1];
-        for (uint32_t i = 0; i < nv; ++i) {
-            const int q = b + 2 * (int)i;
-            const uint32_t r0 = (uint32_t)row[perm[q]];
-            const uint32_t r1p = (q + 1 < e) ? (uint32_t)row[perm[q + 1]] + 1u : 0u;
-            key[base + i] = ((uint64_t)r0 << 32) | r1p;
-            vid[base + i] = base + i;
-            vcol[base + i] = (uint32_t)c;
-            vent[base + i] = (uint32_t)q;
-        }
-    }
-};
-// position p in the regrouped stream: x = starts an item, y = (position valid)
-struct PairLoad {
-    const uint64_t *key;
-    const uint32_t *gstart;      // group start of every position
-    uint32_t chunk;
-    __device__ uint32_t operator()(int64_t p) const { return ((uint32_t)p - gstart[p]) % chunk == 0 ? 1u : 0u; }
-};
-struct GroupStartLoad {          // max-scan of (head ? p + 1 : 0)
-    const uint64_t *key;
-    __device__ uint32_t operator()(int64_t p) const { return (p == 0 || key[p] != key[p - 1]) ? (uint32_t)p + 1u : 0u; }
-};
-struct GroupStartStore {
-    const uint64_t *key;
-    uint32_t *gstart;
-    __device__ void operator()(int64_t p, uint32_t prefix, uint32_t mine) const { gstart[p] = (mine ? mine : prefix) - 1u; }
-};
-struct PairEmit {
-    const uint64_t *key;
-    const uint32_t *vid, *vcol, *vent;   // vid: sorted order -> virtual column
-    const int32_t *colptr;
-    const uint32_t *perm;
-    const double *val;
-    int64_t nv;
-    int chunk;
-    int4 *items;
-    int32_t *pcol;
-    double *pv0, *pv1;
-    uint32_t *fxkey, *fxslot;    // [2*nitems] (row, slot) pairs for the fix-up lists; row = 0xffffffff if unused
-    __device__ void operator()(int64_t p, uint32_t prefix, uint32_t start) const
-    {
-        const uint64_t k = key[p];
-        const uint32_t v = vid[p];
-        const uint32_t c = vcol[v], q = vent[v];
-        pcol[p] = (int32_t)c;
-        pv0[p] = val[perm[q]];
-        pv1[p] = ((int)q + 1 < colptr[c + 1]) ? val[perm[q + 1]] : 0.0;
-        if (!start) return;
-        int64_t e = p + 1;
-        while (e < nv && e - p < chunk && key[e] == k) ++e;
-        const int32_t r0 = (int32_t)(k >> 32), r1 = (int32_t)(uint32_t)k - 1;
-        items[prefix] = make_int4(r0, (int)p, (int)e, (int)(2 * prefix));
-        fxkey[2 * prefix] = (uint32_t)r0; fxslot[2 * prefix] = 2 * prefix;
-        fxkey[2 * prefix + 1] = r1 >= 0 ? (uint32_t)r1 : 0xffffffffu; fxslot[2 * prefix + 1] = 2 * prefix + 1;
-    }
-};
-
-static bool make_pair_plan(Weighted &W, cudaStream_t s)
-{
-    ApplyPlan &P = W.plan;
-    const int64_t nnz = W.nnz, ncol = W.ncol, nrow = W.nrow;
-    if (getenv("IB_SPMM_NOPAIR")) return false;
-    if (nnz < 1024 || 10 * nnz < 14 * ncol || nnz > 3 * ncol) return false;      // need ~2 nonzeros in most columns
-    // CSC view: stable sort of the nonzeros by column
-    DBuf<int32_t> row((size_t)nnz, s), csorted((size_t)nnz, s), colptr((size_t)ncol + 1, s);
-    DBuf<uint32_t> k0((size_t)nnz, s), k1((size_t)nnz, s), p0((size_t)nnz, s), p1((size_t)nnz, s);
-    expand_rows_kernel<<<(unsigned)cdiv(nrow, 128), 128, 0, s>>>(W.rowptr.p, nrow, row.p);
-    IB_LAUNCHED();
-    IB_CUDA(cudaMemcpyAsync(k0.p, W.col.p, nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
-    iota_u32_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(p0.p, nnz);
-    IB_LAUNCHED();
-    const int w1 = radix_sort_pairs<uint32_t, uint32_t>(k0.p, p0.p, k1.p, p1.p, nnz, bits_for(ncol), s);
-    const uint32_t *perm = w1 ? p1.p : p0.p;
-    u32_to_i32_copy_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(w1 ? k1.p : k0.p, nnz, csorted.p);
-    IB_LAUNCHED();
-    colptr.zero();
-    seg_ptr_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(csorted.p, nnz, ncol, colptr.p);
-    IB_LAUNCHED();
-    // virtual columns, regrouped by the pair of rows (r0, r1) they feed
-    ScanState<uint32_t> vs;
-    transform_scan<uint32_t>(vs, ncol, VCountLoad{colptr.p}, AddU32{}, 0u, s);
-    uint32_t nv_u = 0;
-    IB_CUDA(cudaMemcpyAsync(&nv_u, vs.total.p, sizeof nv_u, cudaMemcpyDeviceToHost, s));
-    IB_CUDA(cudaStreamSynchronize(s));
-    const int64_t nv = nv_u;
-    if (nv == 0 || 10 * nv > 7 * nnz) return false;            // not enough sharing to pay for the partial rows
-    DBuf<uint64_t> key0((size_t)nv, s), key1((size_t)nv, s);
-    DBuf<uint32_t> vid0((size_t)nv, s), vid1((size_t)nv, s), vcol((size_t)nv, s), vent((size_t)nv, s), gstart((size_t)nv, s);
-    scan_apply<uint32_t>(vs, VCountLoad{colptr.p}, AddU32{}, 0u, VEmit{colptr.p, perm, row.p, key0.p, vid0.p, vcol.p, vent.p}, s);
-    const int w2 = radix_sort_pairs<uint64_t, uint32_t>(key0.p, vid0.p, key1.p, vid1.p, nv, 32 + bits_for(nrow + 1), s);
-    const uint64_t *key = w2 ? key1.p : key0.p;
-    const uint32_t *vid = w2 ? vid1.p : vid0.p;
-    ScanState<uint32_t> gs, is;
-    transform_scan<uint32_t>(gs, nv, GroupStartLoad{key}, MaxU32{}, 0u, s);
-    scan_apply<uint32_t>(gs, GroupStartLoad{key}, MaxU32{}, 0u, GroupStartStore{key, gstart.p}, s);
-    transform_scan<uint32_t>(is, nv, PairLoad{key, gstart.p, (uint32_t)pair_chunk()}, AddU32{}, 0u, s);
-    uint32_t nitems = 0;
-    IB_CUDA(cudaMemcpyAsync(&nitems, is.total.p, sizeof nitems, cudaMemcpyDeviceToHost, s));
-    IB_CUDA(cudaStreamSynchronize(s));
-    if (nitems == 0 || nv < 12 * (int64_t)nitems) return false;      // row pairs are not shared by enough columns
-    P.pair_nitems = nitems;
-    P.pair_items.alloc(nitems, s);
-    P.pcol.alloc((size_t)nv, s);
-    P.pv0.alloc((size_t)nv, s);
-    P.pv1.alloc((size_t)nv, s);
-    DBuf<uint32_t> fk0(2 * (size_t)nitems, s), fk1(2 * (size_t)nitems, s), fs0(2 * (size_t)nitems, s), fs1(2 * (size_t)nitems, s);
-    scan_apply<uint32_t>(is, PairLoad{key, gstart.p, (uint32_t)pair_chunk()}, AddU32{}, 0u,
-                         PairEmit{key, vid, vcol.p, vent.p, colptr.p, perm, W.val.p, nv, pair_chunk(), P.pair_items.p, P.pcol.p, P.pv0.p, P.pv1.p, fk0.p, fs0.p}, s);
-    // fix-up lists: (row, slot) sorted by row, slots ascending inside a row (stable)
-    const int64_t nfx = 2 * (int64_t)nitems;
-    const int w3 = radix_sort_pairs<uint32_t, uint32_t>(fk0.p, fs0.p, fk1.p, fs1.p, nfx, 32, s);
-    DBuf<int32_t> fxrow((size_t)nfx, s);
-    u32_to_i32_copy_kernel<<<(unsigned)cdiv(nfx, 256), 256, 0, s>>>(w3 ? fk1.p : fk0.p, nfx, fxrow.p);   // 0xffffffff -> -1
-    IB_LAUNCHED();
-    // unused second slots carry row -1 after the cast and sort last (as 0xffffffff); count the valid prefix
-    P.fx_ptr.alloc((size_t)nrow + 1, s);
-    P.fx_ptr.zero();
-    P.fx_slot.alloc((size_t)nfx, s);
-    IB_CUDA(cudaMemcpyAsync(P.fx_slot.p, w3 ? fs1.p : fs0.p, nfx * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-    std::vector<int32_t> hrow((size_t)nfx);
-    fxrow.download(hrow.data(), (size_t)nfx);
-    IB_CUDA(cudaStreamSynchronize(s));
-    int64_t nvalid = nfx;
-    while (nvalid > 0 && hrow[nvalid - 1] < 0) --nvalid;
-    if (nvalid > 0) {
-        seg_ptr_kernel<<<(unsigned)cdiv(nvalid, 256), 256, 0, s>>>(fxrow.p, nvalid, nrow, P.fx_ptr.p);
-        IB_LAUNCHED();
-    }
-    IB_CUDA(cudaStreamSynchronize(s));
-    P.pair = true;
-    return true;
-}
-
-// Y[r] = sum of the partial rows listed for r (fixed order); rows without partials are zero
-template <int VEC>
-__global__ void __launch_bounds__(256) spmm_fixup_list_kernel(const int32_t *__restrict__ fx_ptr, const uint32_t *__restrict__ fx_slot,
-                                                              int64_t nrow, const double *__restrict__ partials, int64_t ldp, int nvar,
-                                                              double *__restrict__ Y, int64_t ldy)
-{
-    const int nv = nvar / VEC;
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t r = t / nv;
-    int f = (int)(t - r * nv) * VEC;
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched with programmatic stream serialization
-    if (r >= nrow) return;
-    const int b = fx_ptr[r], e = fx_ptr[r + 1];
-    double s[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) s[k] = 0.0;
-    int q = b;
-    for (; q + 4 <= e; q += 4) {
-        double p[4][VEC];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const double *pp = partials + (int64_t)fx_slot[q + u] * ldp + f;
-            if (VEC == 2) { double2 tt = __ldcg(reinterpret_cast<const double2 *>(pp)); p[u][0] = tt.x; p[u][VEC - 1] = tt.y; }
-            else p[u][0] = __ldcg(pp);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) s[k] = s[k] + p[u][k];
-    }
-    for (; q < e; ++q) {
-        const double *pp = partials + (int64_t)fx_slot[q] * ldp + f;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) s[k] = s[k] + __ldcg(pp + k);
-    }
-    double *out = Y + r * ldy + f;
-    if (VEC == 2) *reinterpret_cast<double2 *>(out) = make_double2(s[0], s[VEC - 1]);
-    else out[0] = s[0];
-}
 
 // ---- TMA (cp.async.bulk) pipeline -----------------------------------------------------------------------
 constexpr int TMA_ROWS = 4;          // X rows per pipeline stage (amortises the barrier round trip)
 constexpr int TMA_CONSUMERS = 256;   // consumer threads (8 warps); +1 producer warp
 constexpr int TMA_MAX_TW = 2 * TMA_CONSUMERS;   // fields per tile
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 struct SpmmArgs {
     const int4 *items;
     int64_t nunits;
     int ntile, tw, nstage;
     const int32_t *rowptr, *col;
-    const double *val, *val1, *X;     // val1 != nullptr: pair items (two output rows per column chunk)
+    const double *val, *X;
     int64_t ldx;
     int nvar;
     double *Y;
@@ -422,37 +198,13 @@ struct SpmmArgs {
     double *partials;
     int64_t ldp;
     int row_lo, row_hi;           // only items whose first row lies in [row_lo, row_hi) are processed (row-block sharding)
-    // fused fix-up (cooperative launch only): 0 none, 1 split rows (contiguous partial slots), 2 slot lists
-    int fix_mode;
-    const int4 *split_rows;
-    int64_t nfix;                 // rows to finalise
-    const int32_t *fx_ptr;
-    const uint32_t *fx_slot;
-    // balanced static partition: CTA b owns units [ranges[b], ranges[b+1]) (equal numbers of nonzeros); nullptr: strided
-    const int64_t *ranges;
 };
 
-// ranges[b] = first unit whose item starts at or after nonzero  total*b/nblk  (items are ordered by their first nonzero)
-__global__ void unit_ranges_kernel(const int4 *items, int64_t nitems, int ntile, int64_t total, int nblk, int64_t *ranges)
-{
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > nblk) return;
-    if (b == nblk) { ranges[b] = nitems * ntile; return; }
-    const int64_t target = total * b / nblk;
-    int64_t lo = 0, hi = nitems;            // first k with items[k].y >= target
-    while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (items[mid].y >= target) hi = mid; else lo = mid + 1;
-    }
-    ranges[b] = lo * ntile;
-}
-
-// Shared-memory stage = [TMA_ROWS rows of X][header: TMA_ROWS values (+ TMA_ROWS second values)]; the producer
-// also delivers the matrix values of the stage through the header, so consumers touch global memory only to read the
-// (prefetched) item record and to write results.
+// Shared-memory stage = [TMA_ROWS rows of X][header: TMA_ROWS values]; the producer also delivers the matrix values of
+// the stage through the header, so consumers touch global memory only to read the (prefetched) item record and to
+// write results.
 constexpr uint32_t TMA_HDR = 2 * TMA_ROWS * 8;
 
-template <bool PAIR>
 __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const SpmmArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -469,12 +221,12 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
     __syncthreads();
     int stage = 0;
     uint32_t phase = 0;
-    const int64_t ustep = a.ranges ? 1 : (int64_t)gridDim.x;
-    int64_t u = a.ranges ? a.ranges[blockIdx.x] : (int64_t)blockIdx.x;
-    const int64_t uend = a.ranges ? a.ranges[blockIdx.x + 1] : a.nunits;
+    const int64_t ustep = (int64_t)gridDim.x;
+    int64_t u = (int64_t)blockIdx.x;
+    const int64_t uend = a.nunits;
     int4 it_next = u < uend ? a.items[u / a.ntile] : make_int4(0, 0, 0, 0);
     if (warp == TMA_CONSUMERS / 32) {
-        // ===== producer warp: lanes 0..nr-1 each issue one row copy of the stage and post its matrix value(s)
+        // ===== producer warp: lanes 0..nr-1 each issue one row copy of the stage and post its matrix value
         for (; u < uend; u += ustep) {
             const int64_t item = u / a.ntile;
             const int tile = (int)(u - item * a.ntile);
@@ -486,11 +238,10 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
             for (int j = it.y; j < it.z; j += TMA_ROWS) {
                 const int nr = min(TMA_ROWS, it.z - j);
                 int c = 0;
-                double v = 0.0, v1 = 0.0;
+                double v = 0.0;
                 if (lane < nr) {
                     c = __ldg(a.col + j + lane);
                     v = __ldg(a.val + j + lane);
-                    if (PAIR) v1 = __ldg(a.val1 + j + lane);
                 }
                 if (lane == 0) mbar_wait(empty + stage, phase ^ 1u);
                 __syncwarp();
@@ -498,7 +249,6 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
                 if (lane < TMA_ROWS) {
                     double *hdr = reinterpret_cast<double *>(sp + (size_t)TMA_ROWS * rowbytes);
                     hdr[lane] = v;
-                    if (PAIR) hdr[TMA_ROWS + lane] = v1;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_expect_tx(full + stage, tb * (uint32_t)nr);      // arrive (release) after the header stores
@@ -523,7 +273,7 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
             int my_end = (lane < nrows) ? __ldg(a.rowptr + it.x + lane + 1) : 0;
             int cur = 0;
             int cur_end = nrows ? __shfl_sync(0xffffffffu, my_end, 0) : it.z;
-            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            double a0 = 0.0, a1 = 0.0;
             int j = it.y;
             // leading empty rows of a group
             while (cur < nrows && cur_end == j) {
@@ -545,11 +295,6 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
                             const double v = hdr[r];
                             a0 = a0 + v * x.x;
                             a1 = a1 + v * x.y;
-                            if (PAIR) {
-                                const double w = hdr[TMA_ROWS + r];
-                                b0 = b0 + w * x.x;
-                                b1 = b1 + w * x.y;
-                            }
                         }
                         ++j;
                         while (cur < nrows && cur_end == j) {      // row(s) of a group complete
@@ -564,58 +309,9 @@ __global__ void __launch_bounds__(TMA_CONSUMERS + 32) spmm_tma_kernel(const Spmm
                 if (lane == 0) mbar_arrive(empty + stage);
                 if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
             }
-            if (it.w >= 0 && active) {  // chunk: partial sum(s), combined in a fixed order by the fix-up
-                reinterpret_cast<double2 *>(a.partials + (int64_t)it.w * a.ldp + f0)[t] = make_double2(a0, a1);
-                if (PAIR) reinterpret_cast<double2 *>(a.partials + (int64_t)(it.w + 1) * a.ldp + f0)[t] = make_double2(b0, b1);
-            }
+            // chunk of a long row: partial sum, combined in chunk order by the fix-up
+            if (it.w >= 0 && active) reinterpret_cast<double2 *>(a.partials + (int64_t)it.w * a.ldp + f0)[t] = make_double2(a0, a1);
         }
-    }
-    if (a.fix_mode == 0) return;
-    // ---- fused fix-up: the grid is co-resident (cooperative launch), so one grid-wide barrier replaces a kernel
-    // boundary; afterwards every thread sums the partial rows of some (row, field pair) in the fixed slot order
-    __threadfence();
-    cooperative_groups::this_grid().sync();
-    const int nv2 = a.nvar / 2;
-    const int64_t total = a.nfix * nv2;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = idx / nv2;
-        const int f = (int)(idx - r * nv2) * 2;
-        double2 acc = make_double2(0.0, 0.0);
-        int64_t orow;
-        if (a.fix_mode == 1) {
-            const int4 sr = a.split_rows[r];
-            orow = sr.x;
-            if (sr.x < a.row_lo || sr.x >= a.row_hi) continue;
-            const double *pp = a.partials + (int64_t)sr.y * a.ldp + f;
-            int q = 0;
-            for (; q + 4 <= sr.z; q += 4) {
-                double2 p[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) p[k] = __ldcg(reinterpret_cast<const double2 *>(pp + (int64_t)(q + k) * a.ldp));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { acc.x = acc.x + p[k].x; acc.y = acc.y + p[k].y; }
-            }
-            for (; q < sr.z; ++q) {
-                const double2 p = __ldcg(reinterpret_cast<const double2 *>(pp + (int64_t)q * a.ldp));
-                acc.x = acc.x + p.x; acc.y = acc.y + p.y;
-            }
-        } else {
-            orow = r;
-            const int b = a.fx_ptr[r], e = a.fx_ptr[r + 1];
-            int q = b;
-            for (; q + 4 <= e; q += 4) {
-                double2 p[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) p[k] = __ldcg(reinterpret_cast<const double2 *>(a.partials + (int64_t)a.fx_slot[q + k] * a.ldp + f));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { acc.x = acc.x + p[k].x; acc.y = acc.y + p[k].y; }
-            }
-            for (; q < e; ++q) {
-                const double2 p = __ldcg(reinterpret_cast<const double2 *>(a.partials + (int64_t)a.fx_slot[q] * a.ldp + f));
-                acc.x = acc.x + p.x; acc.y = acc.y + p.y;
-            }
-        }
-        *reinterpret_cast<double2 *>(a.Y + orow * a.ldy + f) = acc;
     }
 }
 
@@ -894,158 +590,6 @@ __global__ void __launch_bounds__(GC_WARPS * 32) spmm_gc_kernel(const GcArgs a)
     }
 }
 
-// ---- per-warp streaming kernel for the pair plan (EvI) -------------------------------------------------------------
-// The CTA-wide ring of spmm_tma_kernel is consumer-bound: with fewer CTAs per SM it slows down in proportion (one CTA per
-// SM: 0.41 of peak), so its eight consumer warps, not HBM, set the pace.  Here every warp is its own pipeline, as in
-// spmm_gc_kernel: a warp owns one tile of 64*NQ fields and a CONTIGUOUS run of pair items (equal numbers of columns per
-// warp group, BalanceTable), walks the regrouped column stream record by record across item boundaries, and keeps a ring
-// of PW_R X-row pieces in flight: after a record is consumed its slot is refilled with the piece PW_R records ahead (one
-// bulk async copy issued by lane 0, completing on the slot's own mbarrier).  Column ids and the two values of a column
-// are staged through a small double-buffered shared-memory table, 32 records at a time, loaded one block ahead.  The
-// warps of a CTA work on the same items (one tile each), so the pieces of an X row are requested together.
-struct PwArgs {
-    const int4 *items;            // pair items (r0, begin, end, first partial slot)
-    const int64_t *ranges;        // [ngroup + 1] item ranges of the warp groups
-    int ngroup, ntile;
-    const int32_t *col;
-    const double *v0, *v1, *X;
-    int64_t ldx;
-    int nvar;
-    double *partials;
-    int64_t ldp;
-};
-constexpr int PW_B = 4;           // records per batch (one mbarrier round trip per batch)
-constexpr int PW_NB = 3;          // batches in the ring
-constexpr int PW_R = PW_B * PW_NB;
-constexpr int PW_WARPS = 4;       // warps per CTA
-
-template <int NQ>
-constexpr size_t pw_smem_bytes() { return (size_t)PW_WARPS * (PW_R * 64 * NQ * 8 + 2 * 32 * 24 + 64); }
-
-template <int NQ>
-__global__ void __launch_bounds__(PW_WARPS * 32) spmm_pw_kernel(const PwArgs a)
-{
-    constexpr int TW = 64 * NQ;
-    constexpr uint32_t ROWB = TW * 8;
-    constexpr uint32_t WARPB = PW_R * ROWB + 2 * 32 * 24 + 64;
-    extern __shared__ __align__(128) unsigned char pw_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *base = pw_raw + (size_t)warp * WARPB;
-    unsigned char *ring = base;
-    double *tv0 = reinterpret_cast<double *>(base + PW_R * ROWB);        // [2][32]
-    double *tv1 = tv0 + 64;                                              // [2][32]
-    int32_t *tcol = reinterpret_cast<int32_t *>(tv1 + 64);               // [2][32]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(base + PW_R * ROWB + 2 * 32 * 24);      // [PW_NB]
-    if (lane < PW_NB) mbar_init(bar + lane, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
-    const int64_t gw = (int64_t)blockIdx.x * PW_WARPS + warp;
-    const int group = (int)(gw / a.ntile), tile = (int)(gw % a.ntile);
-    if (group >= a.ngroup) return;
-    const int64_t ib = a.ranges[group], ie = a.ranges[group + 1];
-    if (ib >= ie) return;
-    const int f0 = tile * TW;
-    const uint32_t tb = (uint32_t)min(TW, a.nvar - f0) * 8u;
-    const int nq = min(NQ, (a.nvar - f0 + 63) >> 6);
-    const bool last_live = f0 + 64 * (nq - 1) + 2 * lane < a.nvar;
-    int4 it = __ldg(a.items + ib);
-    const int64_t P0 = it.y;
-    const int64_t n = __ldg(a.items + ie - 1).z - P0;                  // records of this warp
-    const int64_t nb = (n + PW_B - 1) / PW_B;
-    int4 it_next = ib + 1 < ie ? __ldg(a.items + ib + 1) : it;
-    int64_t item = ib;
-
-    // record blocks of 32: lane l holds record 32*j + l of block j
-    auto load_block = [&](int64_t j, int &c, double &x0, double &x1) {
-        const int64_t k = 32 * j + lane;
-        c = 0; x0 = 0.0; x1 = 0.0;
-        if (k < n) { c = __ldg(a.col + P0 + k); x0 = __ldg(a.v0 + P0 + k); x1 = __ldg(a.v1 + P0 + k); }
-    };
-    auto store_block = [&](int64_t j, int c, double x0, double x1) {
-        const int o = (int)(j & 1) * 32 + lane;
-        tcol[o] = c; tv0[o] = x0; tv1[o] = x1;
-    };
-    // X-row pieces of batch b -> ring batch b % PW_NB: lane r < PW_B fetches record PW_B*b + r
-    auto issue_batch = [&](int64_t b) {
-        const int bs = (int)(b % PW_NB);
-        const int64_t k = PW_B * b + lane;
-        const int cnt = (int)min((int64_t)PW_B, n - PW_B * b);
-        if (lane == 0) mbar_expect_tx(bar + bs, tb * (uint32_t)cnt);
-        __syncwarp();
-        if (lane < cnt) {
-            const int c = tcol[(int)((k >> 5) & 1) * 32 + (int)(k & 31)];
-            bulk_g2s(ring + (size_t)(bs * PW_B + lane) * ROWB, a.X + (int64_t)c * a.ldx + f0, tb, bar + bs);
-        }
-    };
-    int rc; double r0v, r1v;
-    load_block(0, rc, r0v, r1v);
-    store_block(0, rc, r0v, r1v);
-    load_block(1, rc, r0v, r1v);
-    __syncwarp();
-    for (int64_t b = 0; b < nb && b < PW_NB; ++b) issue_batch(b);
-    uint32_t phase = 0;
-    double2 acc0[NQ], acc1[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) { acc0[q] = make_double2(0.0, 0.0); acc1[q] = make_double2(0.0, 0.0); }
-    const double2 *xb = reinterpret_cast<const double2 *>(ring) + lane;
-    for (int64_t b = 0; b < nb; ++b) {
-        const int64_t k0 = PW_B * b;
-        if ((k0 & 31) == 0) {           // entering block j: publish block j+1 (its table half was block j-1's), load block j+2
-            const int64_t j = k0 >> 5;
-            __syncwarp();
-            store_block(j + 1, rc, r0v, r1v);
-            load_block(j + 2, rc, r0v, r1v);
-            __syncwarp();
-        }
-        const int bs = (int)(b % PW_NB);
-        mbar_wait(bar + bs, (phase >> bs) & 1u);
-        phase ^= 1u << bs;
-        // all table and ring reads of the batch first, then the arithmetic record by record
-        const int o = (int)((k0 >> 5) & 1) * 32 + (int)(k0 & 31);          // PW_B divides 32: a batch never straddles blocks
-        double v0[PW_B], v1[PW_B];
-        double2 x[PW_B][NQ];
-#pragma unroll
-        for (int r = 0; r < PW_B; ++r) {
-            v0[r] = tv0[o + r];
-            v1[r] = tv1[o + r];
-            const double2 *xr = xb + (bs * PW_B + r) * (TW / 2);
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) x[r][q] = xr[q * 32];
-        }
-#pragma unroll
-        for (int r = 0; r < PW_B; ++r) {
-            if (k0 + r < n) {
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    acc0[q].x = acc0[q].x + v0[r] * x[r][q].x;
-                    acc0[q].y = acc0[q].y + v0[r] * x[r][q].y;
-                    acc1[q].x = acc1[q].x + v1[r] * x[r][q].x;
-                    acc1[q].y = acc1[q].y + v1[r] * x[r][q].y;
-                }
-                if (P0 + k0 + r + 1 == it.z) {      // item complete: its two partial rows (summed in a fixed order by the fix-up)
-                    double2 *p0 = reinterpret_cast<double2 *>(a.partials + (int64_t)it.w * a.ldp + f0) + lane;
-                    double2 *p1 = reinterpret_cast<double2 *>(a.partials + (int64_t)(it.w + 1) * a.ldp + f0) + lane;
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        if (q < nq - 1 || (q == nq - 1 && last_live)) { p0[q * 32] = acc0[q]; p1[q * 32] = acc1[q]; }
-                        acc0[q] = make_double2(0.0, 0.0);
-                        acc1[q] = make_double2(0.0, 0.0);
-                    }
-                    ++item;
-                    it = it_next;
-                    if (item + 1 < ie) it_next = __ldg(a.items + item + 1);
-                }
-            }
-        }
-        // refill the ring batch with the pieces PW_NB batches ahead (the reads above are complete: their values were used)
-        if (b + PW_NB < nb) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            issue_batch(b + PW_NB);
-        }
-    }
-}
-
 // ---- plain-load fallback (small / odd nvar, unaligned buffers) ---------------------------------------------
 // A group of L lanes (power of two) owns one (item, field-tile) unit; lane fl owns VEC consecutive fields.
 template <int VEC>
@@ -1185,8 +729,6 @@ __global__ void cons_v_kernel(const int32_t *colptr, const uint32_t *perm, const
     for (int32_t j = colptr[c]; j < colptr[c + 1]; ++j) { const uint32_t e = perm[j]; s += val[e] * wM[row[e]]; }
     v[c] = s;
 }
-__global__ void expand_rows_kernel(const int32_t *rowptr, int64_t nrow, int32_t *row);
-__global__ void u32_to_i32_copy_kernel(const uint32_t *a, int64_t n, int32_t *b);
 
 static void compute_cons_v(Weighted &W, cudaStream_t s)
 {
@@ -1241,6 +783,27 @@ static void launch_dependent(void (*kern)(KArgs...), unsigned grid, unsigned blo
     IB_LAUNCHED();
 }
 
+// cudaFuncSetAttribute is per device: every device sets the dynamic shared-memory opt-ins on its first apply
+struct DeviceAttrs { bool set = false; int max_smem = 0; };
+static DeviceAttrs &device_attrs()
+{
+    static std::mutex mu;
+    static DeviceAttrs da[IB_MAX_DEVICES];
+    const int dev = device_index();
+    std::lock_guard<std::mutex> lk(mu);
+    DeviceAttrs &d = da[dev];
+    if (!d.set) {
+        IB_CUDA(cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        IB_CUDA(cudaFuncSetAttribute(spmm_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem));
+        IB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem));
+        IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<4>()));
+        IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<2>()));
+        IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<1>()));
+        d.set = true;
+    }
+    return d;
+}
+
 void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY, int64_t ldy, bool force_conservation,
                cudaStream_t s, int64_t row_begin, int64_t row_end)
 {
@@ -1280,35 +843,19 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         ldx = ldxs;
     }
     if (ldx < nvar || ldy < nvar) fail(IB_ERR_ARG, "apply: leading dimension smaller than nvar");
+    // wide matrices with about two nonzeros per column (EvI): one pass over X, no second kernel (apply_stream.cu)
+    if (!ranged && g_tune.use_stream && apply_stream(W, nullptr, dX, ldx, nvar, dY, ldy, nullptr, 0, s)) return;
     make_plan(W, s);
     ApplyPlan &P = W.plan;
     const bool vec2 = (nvar % 2 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && ((uintptr_t)dX % 16 == 0) && ((uintptr_t)dY % 16 == 0);
     const int64_t ldp = (nvar + 1) & ~1;
     DBuf<double> partials((size_t)P.npartials * ldp, s);
-
-    static const int variant = getenv("IB_SPMM_VARIANT") ? atoi(getenv("IB_SPMM_VARIANT")) : 0;   // 0 auto, 1 LDG, 2 TMA
-    static const int want_bps = getenv("IB_SPMM_BPS") ? atoi(getenv("IB_SPMM_BPS")) : 4;            // TMA blocks per SM
-    bool done = false, pair_done = false;
-    static int max_smem_xs = 0;
-    if (!max_smem_xs) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_smem_xs, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        IB_CUDA(cudaFuncSetAttribute(spmm_xs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_xs));
-    }
-    // distinct-column groups: every row has <= GC_S nonzeros (IvE, IvA, EvA); variant 5 forces, others forbid
-    static const int gc_nq = getenv("IB_GC_NQ") ? atoi(getenv("IB_GC_NQ")) : 0;             // 0: by nvar
-    static const int gc_wps = getenv("IB_GC_WPS") ? atoi(getenv("IB_GC_WPS")) : 0;          // warps per SM (0: all that fit)
-    if (P.gc && vec2 && nvar >= 32 && (variant == 0 || variant == 5) && P.gc_nitems * (int64_t)((nvar + 63) / 64) < (int64_t(1) << 31)) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<4>()));
-            IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<2>()));
-            IB_CUDA(cudaFuncSetAttribute(spmm_gc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gc_smem_bytes<1>()));
-            attr_set = true;
-        }
+    DeviceAttrs &da = device_attrs();
+    bool done = false;
+    // distinct-column groups: every row has <= GC_S nonzeros (IvE, IvA, EvA)
+    if (P.gc && vec2 && nvar >= 32 && P.gc_nitems * (int64_t)((nvar + 63) / 64) < (int64_t(1) << 31)) {
         int nq = nvar <= 64 ? 1 : 2;
-        if (gc_nq == 1 || gc_nq == 2 || gc_nq == 4) nq = gc_nq;
+        if (g_tune.gc_nq == 1 || g_tune.gc_nq == 2 || g_tune.gc_nq == 4) nq = g_tune.gc_nq;
         const int tw = 64 * nq;
         const int ntile = (nvar + tw - 1) / tw;
         GcArgs a{P.gc_items.p, P.gc_ucol.p, P.gc_recs.p, P.gc_nitems, ntile, dX, ldx, nvar, dY, ldy, rlo, rhi, P.gc_counter.p};
@@ -1317,7 +864,6 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GC_WARPS * 32, smem);
         occ = std::max(occ, 1);
-        if (gc_wps > 0) occ = std::max(1, std::min(occ, gc_wps / GC_WARPS));
         const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(cdiv(a.nitems * ntile, GC_WARPS), (int64_t)sm_count() * occ));
         if (a.nitems > 0) {
             kern<<<(unsigned)nblk, GC_WARPS * 32, smem, s>>>(a);
@@ -1325,12 +871,11 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         }
         return;
     }
-    // X-stationary path: tall matrix, few columns, no long rows (variant 3 forces it, 4 forbids it)
-    if (vec2 && !ranged && variant != 1 && variant != 2 && variant != 4 && W.ncol > 0 && W.nrow >= 8 * W.ncol && P.max_row_len <= 256 && nvar >= 8 &&
-        (variant == 3 || 2 * W.nnz >= 3 * W.nrow)) {
+    // X-stationary path: tall matrix, few columns, no long rows
+    if (vec2 && !ranged && W.ncol > 0 && W.nrow >= 8 * W.ncol && P.max_row_len <= 256 && nvar >= 8 && 2 * W.nnz >= 3 * W.nrow) {
         int F = 64;
         while (F > nvar) F >>= 1;
-        while (F >= 8 && (size_t)W.ncol * F * 8 > (size_t)max_smem_xs - 1024) F >>= 1;
+        while (F >= 8 && (size_t)W.ncol * F * 8 > (size_t)da.max_smem - 1024) F >>= 1;
         if (F >= 8) {
             const size_t smem = (size_t)W.ncol * F * 8;
             int occ = 0;
@@ -1342,114 +887,25 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
             const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(a.nunits, (int64_t)sm_count() * occ));
             spmm_xs_kernel<<<(unsigned)nblk, XS_THREADS, smem, s>>>(a);
             IB_LAUNCHED();
-            done = true;
-            pair_done = true;      // nothing to fix up
+            return;            // rows are never split: nothing to fix up
         }
     }
-    if (!done && vec2 && nvar >= 64 && variant != 1) {
+    if (vec2 && nvar >= 64) {
         const int tw = std::min(nvar, TMA_MAX_TW);
         const int ntile = (nvar + tw - 1) / tw;
         const int64_t nunits = P.nitems * ntile;
-        static int max_smem = 0;
-        if (!max_smem) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-            IB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-            IB_CUDA(cudaFuncSetAttribute(spmm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        }
+        const int bps = std::max(1, g_tune.tma_bps);
         const size_t stagebytes = (size_t)tw * 8 * TMA_ROWS + TMA_HDR;
-        const size_t budget = (size_t)(max_smem + 1024) / want_bps - 1024 - 256;
+        const size_t budget = (size_t)(da.max_smem + 1024) / bps - 1024 - 256;
         const int nstage = (int)std::min<size_t>(15, budget / stagebytes);
         if (nstage >= 2) {
             const size_t smem = 256 + (size_t)nstage * stagebytes;
-            // measured on B200: the cooperative launch + grid barrier costs a little more than the PDL-launched fix-up kernel
-            static const bool fuse = getenv("IB_SPMM_FUSE") != nullptr;
-            // true residency (registers, shared memory) bounds the grid of a cooperative launch
-            int occ0 = 0, occ1 = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, spmm_tma_kernel<false>, TMA_CONSUMERS + 32, smem);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, spmm_tma_kernel<true>, TMA_CONSUMERS + 32, smem);
-            static const bool balance = getenv("IB_SPMM_NOBALANCE") == nullptr;
-            auto launch = [&](auto kern, int occ, SpmmArgs a, int64_t nun, bool needs_fix, int64_t total_work, BalanceTable *bt) -> bool {
-                const int64_t slots = (int64_t)sm_count() * std::min(want_bps, std::max(occ, 1));
-                const int64_t per = std::max<int64_t>(1, cdiv(nun, slots));
-                int64_t nblk = std::max<int64_t>(1, cdiv(nun, per));
-                if (balance && bt && !ranged && total_work > 0) {
-                    // CTAs own contiguous runs of units holding equal numbers of nonzeros (items differ in size, and with
-                    // 2-4 items per CTA a strided deal leaves some CTAs a whole item short)
-                    nblk = std::max<int64_t>(1, std::min<int64_t>(nun / a.ntile, slots));
-                    if (bt->nblk != nblk || bt->ntile != a.ntile) {
-                        bt->ranges.alloc((size_t)nblk + 1, s);
-                        unit_ranges_kernel<<<(unsigned)cdiv(nblk + 1, 128), 128, 0, s>>>(a.items, nun / a.ntile, a.ntile, total_work, (int)nblk, bt->ranges.p);
-                        IB_LAUNCHED();
-                        bt->nblk = nblk; bt->ntile = a.ntile;
-                    }
-                    a.ranges = bt->ranges.p;
-                }
-                if (needs_fix && fuse && occ >= 1 && nblk <= (int64_t)sm_count() * occ) {
-                    void *kargs[] = {&a};
-                    cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)nblk), dim3(TMA_CONSUMERS + 32), kargs, smem, s);
-                    if (e == cudaSuccess) { IB_LAUNCHED(); return true; }
-                    cudaGetLastError();      // fall through to the two-kernel path
-                }
-                a.fix_mode = 0;
-                kern<<<(unsigned)nblk, TMA_CONSUMERS + 32, smem, s>>>(a);
-                IB_LAUNCHED();
-                return false;
-            };
-            if (P.pair && !ranged) {
-                const int64_t nun = P.pair_nitems * ntile;
-                DBuf<double> pp((size_t)(2 * P.pair_nitems) * ldp, s);
-                SpmmArgs a{P.pair_items.p, nun, ntile, tw, nstage, W.rowptr.p, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, dY, ldy, pp.p, ldp,
-                           0, 0x7fffffff, 2, nullptr, W.nrow, P.fx_ptr.p, P.fx_slot.p, nullptr};
-                static const bool skipfix = getenv("IB_SPMM_SKIPFIX") != nullptr;      // timing experiments only
-                static const int pw = getenv("IB_SPMM_PW") ? atoi(getenv("IB_SPMM_PW")) : 0;       // per-warp streaming kernel
-                bool main_done = false;
-                if (pw > 0 && nvar >= 64) {
-                    static bool pw_attr = false;
-                    if (!pw_attr) {
-                        IB_CUDA(cudaFuncSetAttribute(spmm_pw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_smem_bytes<2>()));
-                        IB_CUDA(cudaFuncSetAttribute(spmm_pw_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_smem_bytes<1>()));
-                        pw_attr = true;
-                    }
-                    const int nq = pw == 1 ? 1 : 2;
-                    const int ptile = (nvar + 64 * nq - 1) / (64 * nq);
-                    const size_t psmem = nq == 2 ? pw_smem_bytes<2>() : pw_smem_bytes<1>();
-                    auto pk = nq == 2 ? spmm_pw_kernel<2> : spmm_pw_kernel<1>;
-                    int pocc = 0;
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, pk, PW_WARPS * 32, psmem);
-                    pocc = std::max(pocc, 1);
-                    const int64_t nwarps = (int64_t)sm_count() * pocc * PW_WARPS;
-                    const int64_t ngroup = std::max<int64_t>(1, std::min<int64_t>(P.pair_nitems, nwarps / ptile));
-                    BalanceTable &bt = P.bal_pw;
-                    if (bt.nblk != ngroup || bt.ntile != 1) {
-                        bt.ranges.alloc((size_t)ngroup + 1, s);
-                        unit_ranges_kernel<<<(unsigned)cdiv(ngroup + 1, 128), 128, 0, s>>>(P.pair_items.p, P.pair_nitems, 1, (int64_t)P.pcol.n, (int)ngroup, bt.ranges.p);
-                        IB_LAUNCHED();
-                        bt.nblk = ngroup; bt.ntile = 1;
-                    }
-                    PwArgs pa{P.pair_items.p, bt.ranges.p, (int)ngroup, ptile, P.pcol.p, P.pv0.p, P.pv1.p, dX, ldx, nvar, pp.p, ldp};
-                    pk<<<(unsigned)cdiv(ngroup * ptile, PW_WARPS), PW_WARPS * 32, psmem, s>>>(pa);
-                    IB_LAUNCHED();
-                    main_done = true;
-                }
-                if (main_done) {
-                    if (!skipfix) {
-                        const int64_t tot = W.nrow * (int64_t)(nvar / 2);
-                        launch_dependent(spmm_fixup_list_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.fx_ptr.p, P.fx_slot.p, W.nrow, pp.p, ldp, nvar, dY, ldy);
-                    }
-                } else if (!launch(spmm_tma_kernel<true>, occ1, a, nun, true, (int64_t)P.pcol.n, &P.bal_pair) && !skipfix) {
-                    const int64_t tot = W.nrow * (int64_t)(nvar / 2);
-                    launch_dependent(spmm_fixup_list_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.fx_ptr.p, P.fx_slot.p, W.nrow, pp.p, ldp, nvar, dY, ldy);
-                }
-                pair_done = true;
-            } else {
-                SpmmArgs a{P.items.p, nunits, ntile, tw, nstage, W.rowptr.p, W.col.p, W.val.p, nullptr, dX, ldx, nvar, dY, ldy, partials.p, ldp,
-                           rlo, rhi, 1, P.split_rows.p, P.nsplit_rows, nullptr, nullptr, nullptr};
-                // equal-size chunks: the strided deal is already even (and measured 3 % faster than contiguous runs on AvI)
-                static const bool balance_rows = getenv("IB_SPMM_BALANCE_ROWS") != nullptr;
-                if (launch(spmm_tma_kernel<false>, occ0, a, nunits, P.nsplit_rows > 0, W.nnz, balance_rows ? &P.bal_rows : nullptr)) pair_done = true;   // fix-up already done
-            }
+            SpmmArgs a{P.items.p, nunits, ntile, tw, nstage, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp, rlo, rhi};
+            const int64_t slots = (int64_t)sm_count() * bps;
+            const int64_t per = std::max<int64_t>(1, cdiv(nunits, slots));
+            const int64_t nblk = std::max<int64_t>(1, cdiv(nunits, per));
+            spmm_tma_kernel<<<(unsigned)nblk, TMA_CONSUMERS + 32, smem, s>>>(a);
+            IB_LAUNCHED();
             done = true;
         }
     }
@@ -1469,7 +925,7 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
             spmm_ldg_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(P.items.p, nunits, ntile, L, W.rowptr.p, W.col.p, W.val.p, dX, ldx, nvar, dY, ldy, partials.p, ldp, rlo, rhi);
         IB_LAUNCHED();
     }
-    if (P.nsplit_rows > 0 && !pair_done && !getenv("IB_SPMM_SKIPFIX")) {
+    if (P.nsplit_rows > 0) {
         if (vec2) {
             int64_t tot = P.nsplit_rows * (nvar / 2);
             launch_dependent(spmm_fixup_kernel<2>, (unsigned)cdiv(tot, 256), 256, 0, s, P.split_rows.p, P.nsplit_rows, partials.p, ldp, nvar, dY, ldy, rlo, rhi);

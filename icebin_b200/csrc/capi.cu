@@ -9,6 +9,7 @@
 namespace ib {
 
 std::atomic<int64_t> g_launches{0};
+Tune g_tune;
 static thread_local std::string g_err;
 
 void ensure_device()
@@ -22,20 +23,35 @@ void ensure_device()
     }
 }
 
+int device_index()
+{
+    int dev = 0;
+    IB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= IB_MAX_DEVICES) fail(IB_ERR_CUDA, "icebin_b200: device index %d out of range", dev);
+    return dev;
+}
+
+// Freed blocks stay in the device's default memory pool up to this many bytes (steady-state matrix builds then never
+// reach the driver allocator); what exceeds it goes back to the driver at the next synchronisation, so a co-resident
+// allocator (the host application's) is not starved.  ib_trim() releases everything.
+constexpr uint64_t POOL_KEEP_BYTES = 2ull << 30;
+
 cudaStream_t default_stream()
 {
     static std::mutex mu;
-    static cudaStream_t streams[64] = {};
-    int dev = 0;
-    IB_CUDA(cudaGetDevice(&dev));
+    static cudaStream_t streams[IB_MAX_DEVICES] = {};
+    const int dev = device_index();
     std::lock_guard<std::mutex> lk(mu);
     if (!streams[dev]) {
         IB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
-        // keep freed blocks in the pool: steady-state matrix builds then never reach the driver allocator
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            uint64_t thr = 0;
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            if (thr < POOL_KEEP_BYTES) {          // never lower a threshold the host application has raised
+                thr = POOL_KEEP_BYTES;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
         }
     }
     return streams[dev];
@@ -43,9 +59,8 @@ cudaStream_t default_stream()
 
 int sm_count()
 {
-    static int n[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
+    static int n[IB_MAX_DEVICES] = {};
+    const int dev = device_index();
     if (!n[dev]) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
     return n[dev] > 0 ? n[dev] : 148;
 }
@@ -159,6 +174,33 @@ int ib_set_device(int device)
     IB_CATCH
 }
 int64_t ib_launch_count(void) { return g_launches.load(); }
+
+/* performance knobs (results never depend on them) */
+int ib_tune(const char *key, int value)
+{
+    IB_TRY
+    if (!key) fail(IB_ERR_ARG, "ib_tune: null key");
+    const std::string k(key);
+    if (k == "stream_bps") { if (value < 1 || value > 8) fail(IB_ERR_ARG, "ib_tune: stream_bps in 1..8"); g_tune.stream_bps = value; }
+    else if (k == "tma_bps") { if (value < 1 || value > 8) fail(IB_ERR_ARG, "ib_tune: tma_bps in 1..8"); g_tune.tma_bps = value; }
+    else if (k == "gc_nq") { if (value != 0 && value != 1 && value != 2 && value != 4) fail(IB_ERR_ARG, "ib_tune: gc_nq in {0,1,2,4}"); g_tune.gc_nq = value; }
+    else if (k == "use_stream") g_tune.use_stream = value != 0;
+    else if (k == "use_gc") g_tune.use_gc = value != 0;
+    else fail(IB_ERR_ARG, "ib_tune: unknown key '%s'", key);
+    return IB_OK;
+    IB_CATCH
+}
+int ib_trim(void)
+{
+    IB_TRY
+    ensure_device();
+    cudaMemPool_t pool;
+    IB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_index()));
+    IB_CUDA(cudaDeviceSynchronize());
+    IB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return IB_OK;
+    IB_CATCH
+}
 
 // ---------------------------------------------------------------------------------------- device buffers
 int ib_dev_alloc(void **out, int64_t bytes)
@@ -520,34 +562,60 @@ int ib_w_apply_dev(const ib_weighted *W, const double *dX, int64_t ldx, int32_t 
     IB_CATCH
 }
 
-// fork/join helper for independent applies
+// Several matrices applied to the same fields.  Two wide matrices (the coupler's EvI + AvI) are stacked and applied in
+// ONE pass over X (apply_stream.cu); anything else forks onto per-call auxiliary streams and joins back on `s`.
+struct ForkJoin {            // per device; used by one host thread at a time (mutex held for the whole fork/join)
+    cudaStream_t aux[7] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[7] = {};
+};
 static void apply_many(int nmat, const ib_weighted *const *W, const double *dX, int64_t ldx, int nvar, double *const *dY,
                        const int64_t *ldy, bool force, cudaStream_t s)
 {
-    static std::mutex mu;
-    static cudaStream_t aux[64][7] = {};
-    static cudaEvent_t fork_ev[64] = {}, join_ev[64][7] = {};
-    int dev = 0;
-    IB_CUDA(cudaGetDevice(&dev));
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (!fork_ev[dev]) {
-            IB_CUDA(cudaEventCreateWithFlags(&fork_ev[dev], cudaEventDisableTiming));
-            for (int i = 0; i < 7; ++i) {
-                IB_CUDA(cudaStreamCreateWithFlags(&aux[dev][i], cudaStreamNonBlocking));
-                IB_CUDA(cudaEventCreateWithFlags(&join_ev[dev][i], cudaEventDisableTiming));
-            }
+    if (nmat > 8) fail(IB_ERR_ARG, "ib_w_apply_many: at most 8 matrices per call");
+    if (nmat == 2 && g_tune.use_stream) {
+        Weighted &a = *W[0]->w, &b = *W[1]->w;
+        const bool plain = !force || (a.conservative && b.conservative);     // no conservation correction involved
+        if (plain && a.nrow > 0 && b.nrow > 0) {
+            const bool a_first = a.nnz >= b.nnz;       // M1 holds the pairs (EvI), M2 the single entries (AvI)
+            Weighted &m1 = a_first ? a : b, &m2 = a_first ? b : a;
+            const int i1 = a_first ? 0 : 1, i2 = 1 - i1;
+            if (apply_stream(m1, &m2, dX, ldx, nvar, dY[i1], ldy[i1], dY[i2], ldy[i2], s)) return;
         }
     }
-    if (nmat > 8) fail(IB_ERR_ARG, "ib_w_apply_many: at most 8 matrices per call");
-    IB_CUDA(cudaEventRecord(fork_ev[dev], s));
-    for (int i = 1; i < nmat; ++i) {
-        IB_CUDA(cudaStreamWaitEvent(aux[dev][i - 1], fork_ev[dev], 0));
-        apply_dev(*W[i]->w, dX, ldx, nvar, dY[i], ldy[i], force, aux[dev][i - 1]);
-        IB_CUDA(cudaEventRecord(join_ev[dev][i - 1], aux[dev][i - 1]));
+    if (nmat == 1) { apply_dev(*W[0]->w, dX, ldx, nvar, dY[0], ldy[0], force, s); return; }
+    static std::mutex mu;
+    static ForkJoin fjs[IB_MAX_DEVICES];
+    const int dev = device_index();
+    std::lock_guard<std::mutex> lk(mu);
+    ForkJoin &fj = fjs[dev];
+    if (!fj.fork_ev) {
+        IB_CUDA(cudaEventCreateWithFlags(&fj.fork_ev, cudaEventDisableTiming));
+        for (int i = 0; i < 7; ++i) {
+            IB_CUDA(cudaStreamCreateWithFlags(&fj.aux[i], cudaStreamNonBlocking));
+            IB_CUDA(cudaEventCreateWithFlags(&fj.join_ev[i], cudaEventDisableTiming));
+        }
     }
-    apply_dev(*W[0]->w, dX, ldx, nvar, dY[0], ldy[0], force, s);
-    for (int i = 1; i < nmat; ++i) IB_CUDA(cudaStreamWaitEvent(s, join_ev[dev][i - 1], 0));
+    IB_CUDA(cudaEventRecord(fj.fork_ev, s));
+    int forked = 0;
+    // whatever happens, `s` waits for every auxiliary stream that was given work before this function returns
+    auto join = [&]() {
+        for (int i = 0; i < forked; ++i) {
+            cudaEventRecord(fj.join_ev[i], fj.aux[i]);
+            cudaStreamWaitEvent(s, fj.join_ev[i], 0);
+        }
+    };
+    try {
+        for (int i = 1; i < nmat; ++i) {
+            IB_CUDA(cudaStreamWaitEvent(fj.aux[i - 1], fj.fork_ev, 0));
+            forked = i;
+            apply_dev(*W[i]->w, dX, ldx, nvar, dY[i], ldy[i], force, fj.aux[i - 1]);
+        }
+        apply_dev(*W[0]->w, dX, ldx, nvar, dY[0], ldy[0], force, s);
+    } catch (...) {
+        join();
+        throw;
+    }
+    join();
 }
 
 int ib_w_apply_many_dev(int32_t nmat, const ib_weighted *const *W, const double *dX, int64_t ldx, int32_t nvar, double *const *dY,

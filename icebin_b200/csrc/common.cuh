@@ -46,6 +46,17 @@ extern std::atomic<int64_t> g_launches;   // kernels launched by this library (i
 
 cudaStream_t default_stream();   // the library's own non-blocking stream (created on first use, per device)
 int sm_count();
+int device_index();              // current device, < IB_MAX_DEVICES
+constexpr int IB_MAX_DEVICES = 64;
+// performance knobs (ib_tune): never change results
+struct Tune {
+    int stream_bps = 4;          // CTAs per SM of spmm_stream_kernel
+    int tma_bps = 4;             // CTAs per SM of spmm_tma_kernel
+    int gc_nq = 0;               // spmm_gc_kernel: 64-field groups per lane (0: by nvar)
+    int use_stream = 1;          // one-pass kernel for wide matrices
+    int use_gc = 1;              // distinct-column group kernel for short-row matrices
+};
+extern Tune g_tune;
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

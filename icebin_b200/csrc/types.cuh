@@ -2,6 +2,7 @@
 #pragma once
 #include <array>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -72,13 +73,6 @@ struct RegridMatrices {
     cudaStream_t stream = nullptr;
 };
 
-// balanced static partition of a plan's units over the CTAs of a launch configuration (apply.cu)
-struct BalanceTable {
-    int64_t nblk = 0;
-    int ntile = 0;
-    DBuf<int64_t> ranges;   // [nblk + 1]
-};
-
 // SpMM work decomposition (apply.cu): groups of short rows + chunks of long rows.  One apply at a time per matrix.
 struct ApplyPlan {
     bool ready = false;
@@ -89,16 +83,6 @@ struct ApplyPlan {
     int64_t npartials = 0;
     DBuf<int32_t> slot_srow; // partial slot -> split-row index
     int max_row_len = 0;     // longest row (X-stationary kernel eligibility)
-    // pair-grouped column plan (matrices with <= 2 nonzeros per column, e.g. EvI): columns sharing the same pair
-    // of rows are chunked together so that each X row is read once and feeds both output rows
-    bool pair = false;
-    int64_t pair_nitems = 0;
-    DBuf<int4> pair_items;   // (r0, begin, end, first partial slot = 2*item) over the regrouped column stream
-    DBuf<int32_t> pcol;      // regrouped column ids
-    DBuf<double> pv0, pv1;   // values of the column's first / second nonzero (0 if none)
-    DBuf<int32_t> fx_ptr;    // [nrow+1] partial slots of each output row ...
-    DBuf<uint32_t> fx_slot;  // ... in a fixed order
-    BalanceTable bal_rows, bal_pair, bal_pw;
     // distinct-column groups (matrices whose rows all have <= GC_S nonzeros, e.g. IvE, IvA): see gc_plan.cuh
     bool gc = false;
     int64_t gc_nitems = 0;
@@ -107,6 +91,23 @@ struct ApplyPlan {
     DBuf<int4> gc_recs;      // GcRec (value, slot, flags) per nonzero in row order, one dummy per empty row
     DBuf<unsigned long long> gc_counter;   // dynamic unit counter of the kernel (one apply at a time per matrix)
 };
+
+// One-pass plan for wide matrices, alone or stacked with a partner that shares the input space (apply_stream.cu)
+struct StreamPlan {
+    bool tried = false, ok = false, fresh = true;
+    uint64_t partner_uid = 0;   // uid of the stacked partner (0: none)
+    int R = 0;                  // runs (one per CTA and field tile)
+    int64_t nrec = 0, nev = 0, nslots = 0, nzrows = 0, nrow1 = 0, nrowS = 0;
+    DBuf<int4> recs;            // StRec, two int4 each
+    DBuf<int4> events;          // (stacked row, partial slot or -1, first entry of the row's slot list, slots of the row)
+    DBuf<int32_t> run_ev0;      // [R+1] first event of every run
+    DBuf<uint32_t> fx_slot;     // slot lists, row by row, stream order inside a row
+    DBuf<int32_t> zrows;        // rows without any entry
+    DBuf<int> counters;         // completion counters [nrowS][field tile][consumer warp]; all zero between launches
+    DBuf<double> partials;      // [nslots][ldp]
+};
+
+uint64_t next_uid();
 
 // linear::Weighted_Eigen: CSR matrix (rows = output space) + weights + dims.
 struct Weighted {
@@ -120,6 +121,8 @@ struct Weighted {
     Dim *dims[2] = {nullptr, nullptr};
     std::unique_ptr<Dim> owned[2];
     ApplyPlan plan;
+    StreamPlan stream_plan;
+    uint64_t uid = next_uid();   // identifies the matrix in plans that involve a partner
     cudaStream_t stream = nullptr;
 };
 
@@ -132,5 +135,8 @@ void smooth_rows(RegridMatrices &rm, Weighted &W, Params const &p);
 // apply.cu
 void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY, int64_t ldy, bool force_conservation,
                cudaStream_t s, int64_t row_begin = 0, int64_t row_end = -1);
+// apply_stream.cu: [Y1; Y2] = [M1; M2] X in one pass over X (M2 may be null); false = the pair does not qualify
+bool apply_stream(Weighted &M1, Weighted *M2, const double *dX, int64_t ldx, int nvar, double *dY1, int64_t ldy1, double *dY2,
+                  int64_t ldy2, cudaStream_t s);
 
 }   // namespace ib

@@ -51,6 +51,12 @@ int ib_device_count(void);
 int ib_set_device(int device);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 int64_t ib_launch_count(void);
+/* Performance knobs; results never depend on them.  Keys: "stream_bps", "tma_bps" (CTAs per SM of the one-pass / ring
+ * SpMM kernels, 1..8), "gc_nq" (64-field groups per lane of the distinct-column kernel: 0 = by nvar, 1, 2, 4),
+ * "use_stream", "use_gc" (0 = route around the one-pass kernel / the distinct-column kernel). */
+int ib_tune(const char *key, int value);
+/* Return the device memory the library's stream-ordered allocations cached (cudaMemPoolTrimTo); synchronises the device. */
+int ib_trim(void);
 
 /* Device buffers for hosts that do not link the CUDA runtime themselves (include/icebin/coupler_b200.hpp keeps the
  * coupling fields in HBM between the variable transformation and the regrid applies).  Stream-ordered on the library's

@@ -202,16 +202,32 @@ def test_row_block_sharding(cfg2, spec, nvar):
 
 
 def test_apply_many_matches_single_applies(cfg2):
-    """ib_w_apply_many: EvI and AvI on the same fields, concurrently; identical to the one-at-a-time results."""
+    """ib_w_apply_many: EvI and AvI on the same fields.  The pair is applied in one pass over X (apply_stream.cu), whose
+    sums are associated differently from the one-at-a-time kernels': equal to rounding, and deterministic."""
+    import scipy.sparse
     from icebin_b200 import api
     gg = make_gpu(cfg2)
     rm = gg.regrid_matrices(cfg2["sheets"][0].name, cfg2["elevmask"][0], scale=True, correctA=True)
     EvI, AvI = rm.matrix("EvI"), rm.matrix("AvI")
     X = np.random.default_rng(0).uniform(-1, 1, (EvI.shape[1], 64))
+    absX = np.abs(X)
     for rep in range(3):
         YE, YA = api.apply_many([EvI, AvI], X, layout="cell")
-        assert np.array_equal(YE, EvI.apply(X, layout="cell")) and np.array_equal(YA, AvI.apply(X, layout="cell"))
+        for M, Y in ((EvI, YE), (AvI, YA)):
+            r, c, v = M.to_coo_dense()
+            A = scipy.sparse.csr_matrix((np.abs(v), (r, c)), shape=M.shape)
+            assert np.all(np.abs(Y - M.apply(X, layout="cell")) <= 2e-12 * (A @ absX) + 1e-300)
+        if rep:
+            assert np.array_equal(YE, YE0) and np.array_equal(YA, YA0)
+        YE0, YA0 = YE, YA
     YEf, YAf = api.apply_many([EvI, AvI], np.ascontiguousarray(X.T), layout="field")
     assert np.array_equal(YEf.T, YE) and np.array_equal(YAf.T, YA)
+    # three matrices: forked streams, identical to the single applies
+    api.tune("use_stream", 0)
+    try:
+        YE1, YA1 = api.apply_many([EvI, AvI], X, layout="cell")
+        assert np.array_equal(YE1, EvI.apply(X, layout="cell")) and np.array_equal(YA1, AvI.apply(X, layout="cell"))
+    finally:
+        api.tune("use_stream", 1)
     with pytest.raises(api.IceBinError):
         api.apply_many([EvI, rm.matrix("IvE")], X, layout="cell")      # different input spaces

@@ -31,10 +31,15 @@ def apply_sass():
         pytest.skip("cuobjdump not available")
     from icebin_b200 import build
     build.build()
-    obj = os.path.join(ROOT, "icebin_b200", "build", "apply.o")
-    if not os.path.exists(obj):
-        pytest.skip("object files not kept")
-    return sass_by_function(obj)
+    outs, funcs = "", {}
+    for unit in ("apply.o", "apply_stream.o"):
+        obj = os.path.join(ROOT, "icebin_b200", "build", unit)
+        if not os.path.exists(obj):
+            pytest.skip("object files not kept")
+        o, f = sass_by_function(obj)
+        outs += o
+        funcs.update(f)
+    return outs, funcs
 
 
 def test_only_sm100a_code(apply_sass):
@@ -43,7 +48,7 @@ def test_only_sm100a_code(apply_sass):
     assert archs == {"sm_100a"}, archs
 
 
-@pytest.mark.parametrize("kernel", ["spmm_gc_kernel", "spmm_tma_kernel", "spmm_pw_kernel"])
+@pytest.mark.parametrize("kernel", ["spmm_gc_kernel", "spmm_tma_kernel", "spmm_stream_kernel"])
 def test_bulk_async_copies_and_mbarriers(apply_sass, kernel):
     _, funcs = apply_sass
     mine = {k: v for k, v in funcs.items() if kernel in k}
