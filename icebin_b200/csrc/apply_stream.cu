@@ -41,15 +41,16 @@
 namespace ib {
 
 constexpr int ST_ROWS = 4;              // records (X rows) per pipeline stage
-constexpr int ST_HDR = 128;             // stage header: v0[4] v1[4] v2[4] flags[4]
+constexpr int ST_HDR = 64 * ST_ROWS;     // stage header: the stage's records, verbatim
 constexpr int ST_MAXN1 = 16, ST_MAXN2 = 8;   // nonzeros per column the plan accepts (M1, M2)
 // record flags
 constexpr uint32_t SF_CLOSE = 1u;       // bits 0..2: accumulator k restarts from zero after this record
 constexpr uint32_t SF_SHIFT = 8u;       // bit 3: after the closes, accumulator 1 becomes accumulator 0
 constexpr uint32_t SF_EVENT = 16u;      // bits 4..6: accumulator k is delivered (an event) before it restarts
 
-struct alignas(16) StRec { double v0, v1, v2; int32_t col; uint32_t flags; };
-static_assert(sizeof(StRec) == 32, "StRec is two int4");
+// 64 bytes: values, column, flags and the (row, partial slot or -1) of the up to three sums that end with the record
+struct alignas(16) StRec { double v0, v1, v2; int32_t col; uint32_t flags; int2 ev[3]; int2 pad; };
+static_assert(sizeof(StRec) == 64, "StRec is four int4");
 
 __host__ __device__ inline int64_t run_begin(int64_t n, int64_t R, int64_t b) { return n * b / R; }
 
@@ -135,6 +136,7 @@ __global__ void st_emit_kernel(StackView v, int64_t ncol, const uint32_t *colptr
         r.col = (int32_t)c;
         r.flags = 0;
         r.v0 = r.v1 = r.v2 = 0.0;
+        r.ev[0] = r.ev[1] = r.ev[2] = r.pad = make_int2(-1, -1);
         uint64_t r0 = 0, r1 = 0, r2 = 0;        // row + 1; 0 = none
         if (2 * i < n1) { r0 = (k[2 * i] >> 32) + 1; r.v0 = v.val((uint32_t)k[2 * i]); }
         if (2 * i + 1 < n1) { r1 = (k[2 * i + 1] >> 32) + 1; r.v1 = v.val((uint32_t)k[2 * i + 1]); }
@@ -190,23 +192,20 @@ struct StFlagEmit {
     const uint32_t *vid;
     const StRec *urec;
     StRec *rec;
-    uint32_t *evrow, *evid;
-    int32_t *run_ev0;
-    __device__ void operator()(int64_t p, uint32_t prefix, uint32_t cnt) const
+    int32_t *cols;
+    uint32_t *evrow, *evpos;        // event e: its row; where it lives (record * 4 + accumulator)
+    __device__ void operator()(int64_t p, uint32_t prefix, uint32_t) const
     {
         const uint32_t f = L.flags(p);
         StRec r = urec[vid[p]];
         r.flags = f;
         rec[p] = r;
+        cols[p] = r.col;
         const StRows c = st_rows(L.key[p], L.b1, L.nrow1);
         uint32_t e = prefix;
-        if (f & SF_EVENT) { evrow[e] = (uint32_t)c.r0; evid[e] = e; ++e; }
-        if (f & (SF_EVENT << 1)) { evrow[e] = (uint32_t)c.r1; evid[e] = e; ++e; }
-        if (f & (SF_EVENT << 2)) { evrow[e] = (uint32_t)c.r2; evid[e] = e; ++e; }
-        // first record of a run: where the run's events start
-        const int64_t run = ((p + 1) * L.R + L.n - 1) / L.n - 1;
-        if (run_begin(L.n, L.R, run) == p) run_ev0[run] = (int32_t)prefix;
-        if (p + 1 == L.n) run_ev0[L.R] = (int32_t)(prefix + cnt);
+        if (f & SF_EVENT) { evrow[e] = (uint32_t)c.r0; evpos[e] = (uint32_t)p * 4u; ++e; }
+        if (f & (SF_EVENT << 1)) { evrow[e] = (uint32_t)c.r1; evpos[e] = (uint32_t)p * 4u + 1u; ++e; }
+        if (f & (SF_EVENT << 2)) { evrow[e] = (uint32_t)c.r2; evpos[e] = (uint32_t)p * 4u + 2u; ++e; }
     }
 };
 // events sorted by row: q-th sorted event; x = needs a partial slot, y = row without any event before it ... (zero rows)
@@ -219,16 +218,15 @@ struct StSlotLoad {
     }
 };
 struct StSlotEmit {
-    const int32_t *srow, *fx_ptr;
-    const uint32_t *sev;
-    int4 *events;
+    const int32_t *srow;
+    const uint32_t *spos;           // sorted event q lives at record spos[q] / 4, accumulator spos[q] % 4
+    StRec *rec;
     uint32_t *fx_slot;
     __device__ void operator()(int64_t q, uint32_t prefix, uint32_t multi) const
     {
-        const int32_t r = srow[q];
-        const int32_t b = fx_ptr[r], cnt = fx_ptr[r + 1] - b;
         fx_slot[q] = multi ? prefix : 0xffffffffu;
-        events[sev[q]] = make_int4(r, multi ? (int32_t)prefix : -1, b, cnt);
+        const uint32_t pos = spos[q];
+        rec[pos >> 2].ev[pos & 3u] = make_int2(srow[q], multi ? (int32_t)prefix : -1);
     }
 };
 struct StZeroLoad {
@@ -253,11 +251,11 @@ uint64_t next_uid() { return g_uid.fetch_add(1); }
 static bool make_stream_plan(StreamPlan &P, Weighted &M1, Weighted *M2, int R, cudaStream_t s)
 {
     const uint64_t puid = M2 ? M2->uid : 0;
-    if (P.tried && P.partner_uid == puid && (!P.ok || P.R == R)) return P.ok;
+    if (P.tried && P.partner_uid == puid && (!P.ok || P.R_asked == R)) return P.ok;
     P = StreamPlan();
     P.tried = true;
     P.partner_uid = puid;
-    P.R = R;
+    P.R = P.R_asked = R;
     const int64_t ncol = M1.ncol, nnz1 = M1.nnz, nnz2 = M2 ? M2->nnz : 0, nnz = nnz1 + nnz2;
     const int64_t nrow1 = M1.nrow, nrow2 = M2 ? M2->nrow : 0, nrowS = nrow1 + nrow2;
     const int b1 = bits_for(nrow1 + 2), b2 = bits_for(nrow2 + 2);
@@ -301,15 +299,17 @@ static bool make_stream_plan(StreamPlan &P, Weighted &M1, Weighted *M2, int R, c
     IB_CUDA(cudaStreamSynchronize(s));
     P.nrec = nrec;
     P.nev = nev;
-    P.recs.alloc((size_t)nrec * 2, s);
-    P.run_ev0.alloc((size_t)R + 1, s);
-    P.events.alloc((size_t)nev + 1, s);
+    P.recs.alloc((size_t)nrec * 4, s);
+    P.cols.alloc((size_t)nrec, s);
     P.fx_slot.alloc((size_t)nev + 1, s);
+    if (nrec * 4 >= (int64_t(1) << 32)) return false;
     DBuf<uint32_t> er0((size_t)nev + 1, s), er1((size_t)nev + 1, s), ei0((size_t)nev + 1, s), ei1((size_t)nev + 1, s);
-    scan_apply<uint32_t>(es, FL, AddU32{}, 0u, StFlagEmit{FL, vid, urec.p, reinterpret_cast<StRec *>(P.recs.p), er0.p, ei0.p, P.run_ev0.p}, s);
+    scan_apply<uint32_t>(es, FL, AddU32{}, 0u, StFlagEmit{FL, vid, urec.p, reinterpret_cast<StRec *>(P.recs.p), P.cols.p, er0.p, ei0.p}, s);
     // per-row slot lists: events sorted by row, stream order inside a row (the sort is stable)
     const int w2 = radix_sort_pairs<uint32_t, uint32_t>(er0.p, ei0.p, er1.p, ei1.p, nev, bits_for(nrowS), s);
-    DBuf<int32_t> srow((size_t)nev + 1, s), fx_ptr((size_t)nrowS + 1, s);
+    DBuf<int32_t> srow((size_t)nev + 1, s);
+    DBuf<int32_t> &fx_ptr = P.fx_ptr;
+    fx_ptr.alloc((size_t)nrowS + 1, s);
     fx_ptr.zero();
     if (nev > 0) {
         st_u32_to_i32_kernel<<<(unsigned)cdiv(nev, 256), 256, 0, s>>>(w2 ? er1.p : er0.p, nev, srow.p);
@@ -320,7 +320,7 @@ static bool make_stream_plan(StreamPlan &P, Weighted &M1, Weighted *M2, int R, c
     ScanState<uint32_t> ss, zs;
     transform_scan<uint32_t>(ss, nev, StSlotLoad{srow.p, fx_ptr.p}, AddU32{}, 0u, s);
     scan_apply<uint32_t>(ss, StSlotLoad{srow.p, fx_ptr.p}, AddU32{}, 0u,
-                         StSlotEmit{srow.p, fx_ptr.p, w2 ? ei1.p : ei0.p, P.events.p, P.fx_slot.p}, s);
+                         StSlotEmit{srow.p, w2 ? ei1.p : ei0.p, reinterpret_cast<StRec *>(P.recs.p), P.fx_slot.p}, s);
     transform_scan<uint32_t>(zs, nrowS, StZeroLoad{fx_ptr.p}, AddU32{}, 0u, s);
     uint32_t nslots = 0, nz = 0;
     IB_CUDA(cudaMemcpyAsync(&nslots, ss.total.p, sizeof nslots, cudaMemcpyDeviceToHost, s));
@@ -338,11 +338,11 @@ static bool make_stream_plan(StreamPlan &P, Weighted &M1, Weighted *M2, int R, c
 
 // ---- kernel ----------------------------------------------------------------------------------------------
 struct StreamArgs {
-    const int4 *recs;
+    const int4 *recs;           // StRec
+    const int32_t *cols;        // column of every record (the producer needs nothing else)
     int64_t nrec;
     int R, ntile, tw, nstage;
-    const int4 *events;
-    const int32_t *run_ev0;
+    const int32_t *fx_ptr;
     const uint32_t *fx_slot;
     const double *X;
     int64_t ldx;
@@ -359,8 +359,57 @@ struct StreamArgs {
     int nzrows;
 };
 
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Signals the partial sums a warp has stored since its last flush (lane i holds the i-th: row, slot) and finishes the rows
+// whose last slot this is.  ONE release fence and one round of atomics for the whole batch: a fence per sum stalled
+// the warp for microseconds each time (the memory system is saturated with bulk copies), this runs once or twice per
+// run.  The warp that brings a row's last slot adds the row's slots in slot order and writes Y.
+__device__ __noinline__ void st_flush(const StreamArgs &a, int2 pend, int npend, int f, int strip, int nstrip, bool active)
+{
+    const int lane = threadIdx.x & 31;
+    const bool has = lane < npend;
+    const int32_t r = has ? pend.x : 0;
+    const int fb = has ? __ldg(a.fx_ptr + r) : 0;
+    const int fn = has ? __ldg(a.fx_ptr + r + 1) - fb : 0;
+    fence_gpu();                                    // every lane's partial stores, before any lane's signal
+    __syncwarp();
+    int *cnt = a.counters + (int64_t)r * nstrip + strip;
+    const int old = has ? atomicAdd(cnt, 1) : -2;
+    const bool last = has && old == fn - 1;
+    unsigned todo = __ballot_sync(0xffffffffu, last);
+    if (todo == 0u) return;
+    fence_gpu();
+    if (last) *cnt = 0;                             // ready for the next launch
+    const double *pb = a.partials + f;
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int32_t ri = __shfl_sync(0xffffffffu, r, i);
+        const int fbi = __shfl_sync(0xffffffffu, fb, i), fni = __shfl_sync(0xffffffffu, fn, i);
+        double2 t = make_double2(0.0, 0.0);
+        for (int q0 = 0; q0 < fni; q0 += 32) {
+            const int m = min(32, fni - q0);
+            const uint32_t mine = lane < m ? __ldg(a.fx_slot + fbi + q0 + lane) : 0u;
+            for (int k0 = 0; k0 < m; k0 += 4) {
+                double2 p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t sl = __shfl_sync(0xffffffffu, mine, (k0 + u) & 31);
+                    p[u] = (k0 + u < m && active) ? __ldcg(reinterpret_cast<const double2 *>(pb + (int64_t)sl * a.ldp)) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u < m) { t.x = t.x + p[u].x; t.y = t.y + p[u].y; }
+            }
+        }
+        double *y = (ri < a.nrow1 ? a.Y1 + (int64_t)ri * a.ldy1 : a.Y2 + (int64_t)(ri - a.nrow1) * a.ldy2) + f;
+        if (active) *reinterpret_cast<double2 *>(y) = t;
+    }
+}
+
 template <int NACC>
-__global__ void __launch_bounds__(288) spmm_stream_kernel(const StreamArgs a)
+__global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_constant__ StreamArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
@@ -377,51 +426,39 @@ __global__ void __launch_bounds__(288) spmm_stream_kernel(const StreamArgs a)
     }
     __syncthreads();
     const int run = (int)(blockIdx.x / (unsigned)a.ntile), tile = (int)(blockIdx.x % (unsigned)a.ntile);
-    const int64_t jb = run_begin(a.nrec, a.R, run), je = run_begin(a.nrec, a.R, run + 1);
+    const int jb = (int)run_begin(a.nrec, a.R, run), je = (int)run_begin(a.nrec, a.R, run + 1);      // nrec < 2^31
     const int f0 = tile * a.tw;
     const int live = min(a.tw, a.nvar - f0);        // fields of this tile
     int stage = 0;
     uint32_t phase = 0;
     if (warp == ncw) {
-        // ===== producer warp: lane r < ST_ROWS owns row r of every stage
+        // ===== producer warp: lane r < ST_ROWS copies X row r of the stage, lane ST_ROWS the stage's records
         const uint32_t tb = (uint32_t)live * 8u;
-        int4 ra = make_int4(0, 0, 0, 0), rb = ra;
-        if (lane < ST_ROWS && jb + lane < je) { ra = __ldg(a.recs + 2 * (jb + lane)); rb = __ldg(a.recs + 2 * (jb + lane) + 1); }
+        int c_next = (lane < ST_ROWS && jb + lane < je) ? __ldg(a.cols + jb + lane) : 0;
         pdl_wait();                                 // X may be the previous kernel's output
-        for (int64_t j = jb; j < je; j += ST_ROWS) {
-            const int nr = (int)min((int64_t)ST_ROWS, je - j);
-            const int4 ca = ra, cb = rb;
-            const int64_t jn = j + ST_ROWS + lane;
-            if (lane < ST_ROWS && jn < je) { ra = __ldg(a.recs + 2 * jn); rb = __ldg(a.recs + 2 * jn + 1); }
-            if (lane == 0) mbar_wait(empty + stage, phase ^ 1u);
-            __syncwarp();
+        for (int j = jb; j < je; j += ST_ROWS) {
+            const int nr = min(ST_ROWS, je - j);
+            const int c = c_next;
+            const int jn = j + ST_ROWS + lane;
+            if (lane < ST_ROWS && jn < je) c_next = __ldg(a.cols + jn);
             unsigned char *sp = data + (size_t)stage * stagebytes;
-            if (lane < nr) {
-                double *hdr = reinterpret_cast<double *>(sp + (size_t)ST_ROWS * rowbytes);
-                hdr[lane] = __hiloint2double(ca.y, ca.x);
-                hdr[ST_ROWS + lane] = __hiloint2double(ca.w, ca.z);
-                hdr[2 * ST_ROWS + lane] = __hiloint2double(cb.y, cb.x);
-                reinterpret_cast<uint32_t *>(hdr + 3 * ST_ROWS)[lane] = (uint32_t)cb.w;
+            if (lane == 0) {
+                mbar_wait(empty + stage, phase ^ 1u);
+                mbar_expect_tx(full + stage, (tb + 64u) * (uint32_t)nr);
             }
             __syncwarp();
-            if (lane == 0) mbar_expect_tx(full + stage, tb * (uint32_t)nr);      // arrive (release) after the header stores
-            __syncwarp();
-            if (lane < nr) bulk_g2s(sp + (size_t)lane * rowbytes, a.X + (int64_t)cb.z * a.ldx + f0, tb, full + stage);
+            if (lane < nr) bulk_g2s(sp + (size_t)lane * rowbytes, a.X + (int64_t)c * a.ldx + f0, tb, full + stage);
+            else if (lane == ST_ROWS) bulk_g2s(sp + (size_t)ST_ROWS * rowbytes, a.recs + 4 * (int64_t)j, 64u * (uint32_t)nr, full + stage);
             if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
         }
         return;
     }
     // ===== consumer warps: lane owns fields f0 + 64*warp + 2*lane, +1
-    const int fo = 64 * warp + 2 * lane;            // offset inside the tile
+    const int fo = 64 * warp + 2 * lane;            // offset inside the tile (< tw: always inside the row buffer)
     const bool active = fo < live;
-    int ev_idx = __ldg(a.run_ev0 + run);
-    const int ev_end = __ldg(a.run_ev0 + run + 1);
-    int4 ev_next = ev_idx < ev_end ? __ldg(a.events + ev_idx) : make_int4(0, 0, 0, 0);
-    int *cnt_base = a.counters + (int64_t)tile * ncw + warp;
-    const int64_t cnt_stride = (int64_t)a.ntile * ncw;
     pdl_wait();                                     // nothing is written before the previous kernel has completed
-    // rows without any event are zero
-    for (int64_t z = (int64_t)run * ncw + warp; z < a.nzrows; z += (int64_t)a.R * ncw) {
+    // rows without any entry are zero
+    for (int z = run; z < a.nzrows; z += a.R) {       // every consumer warp zeroes its own strip of the row
         const int32_t r = __ldg(a.zrows + z);
         double *y = r < a.nrow1 ? a.Y1 + (int64_t)r * a.ldy1 : a.Y2 + (int64_t)(r - a.nrow1) * a.ldy2;
         if (active) *reinterpret_cast<double2 *>(y + f0 + fo) = make_double2(0.0, 0.0);
@@ -429,71 +466,69 @@ __global__ void __launch_bounds__(288) spmm_stream_kernel(const StreamArgs a)
     double2 acc[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) acc[k] = make_double2(0.0, 0.0);
-
-    auto deliver = [&](const double2 &sum) {
-        const int4 ev = ev_next;
-        ++ev_idx;
-        if (ev_idx < ev_end) ev_next = __ldg(a.events + ev_idx);
-        const int32_t r = ev.x;
-        double *y = (r < a.nrow1 ? a.Y1 + (int64_t)r * a.ldy1 : a.Y2 + (int64_t)(r - a.nrow1) * a.ldy2) + f0 + fo;
-        if (ev.y < 0) {                             // the row's only event
-            if (active) *reinterpret_cast<double2 *>(y) = sum;
-            return;
-        }
-        if (active) *reinterpret_cast<double2 *>(a.partials + (int64_t)ev.y * a.ldp + f0 + fo) = sum;
-        __threadfence();
-        __syncwarp();
-        int old = 0;
-        if (lane == 0) old = atomicAdd(cnt_base + (int64_t)r * cnt_stride, 1);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old != ev.w - 1) return;
-        // last slot of this (row, strip): add the row's slots in slot order
-        __threadfence();
-        if (lane == 0) cnt_base[(int64_t)r * cnt_stride] = 0;        // ready for the next launch
-        double2 t = make_double2(0.0, 0.0);
-        const double *pb = a.partials + f0 + fo;
-        for (int q0 = 0; q0 < ev.w; q0 += 32) {
-            const int m = min(32, ev.w - q0);
-            const uint32_t mine = lane < m ? __ldg(a.fx_slot + ev.z + q0 + lane) : 0u;
-            for (int k0 = 0; k0 < m; k0 += 4) {
-                double2 p[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t sl = __shfl_sync(0xffffffffu, mine, (k0 + u) & 31);
-                    p[u] = (k0 + u < m && active) ? __ldcg(reinterpret_cast<const double2 *>(pb + (int64_t)sl * a.ldp)) : make_double2(0.0, 0.0);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k0 + u < m) { t.x = t.x + p[u].x; t.y = t.y + p[u].y; }
-            }
-        }
-        if (active) *reinterpret_cast<double2 *>(y) = t;
-    };
-
-    for (int64_t j = jb; j < je; j += ST_ROWS) {
-        const int nr = (int)min((int64_t)ST_ROWS, je - j);
+    int2 pend = make_int2(0, 0);                    // lane i: the i-th partial sum stored since the last flush
+    int npend = 0;
+    for (int j = jb; j < je; j += ST_ROWS) {
+        const int nr = min(ST_ROWS, je - j);
         mbar_wait(full + stage, phase);
         const unsigned char *sb = data + (size_t)stage * stagebytes;
-        const double *hdr = reinterpret_cast<const double *>(sb + (size_t)ST_ROWS * rowbytes);
+        const unsigned char *hdr = sb + (size_t)ST_ROWS * rowbytes;
         const unsigned char *sp = sb + (size_t)fo * 8;
+        // second quarter of every record: v2, column, flags
+        int4 h1[ST_ROWS];
 #pragma unroll
-        for (int r = 0; r < ST_ROWS; ++r) {
-            if (r < nr) {
-                const double2 x = active ? *reinterpret_cast<const double2 *>(sp + (size_t)r * rowbytes) : make_double2(0.0, 0.0);
-                const double v0 = hdr[r], v1 = hdr[ST_ROWS + r];
-                const uint32_t fl = reinterpret_cast<const uint32_t *>(hdr + 3 * ST_ROWS)[r];
-                acc[0].x = acc[0].x + v0 * x.x; acc[0].y = acc[0].y + v0 * x.y;
-                acc[1].x = acc[1].x + v1 * x.x; acc[1].y = acc[1].y + v1 * x.y;
+        for (int r = 0; r < ST_ROWS; ++r) h1[r] = *reinterpret_cast<const int4 *>(hdr + 64 * r + 16);
+        uint32_t any = 0;
+#pragma unroll
+        for (int r = 0; r < ST_ROWS; ++r) any |= (uint32_t)h1[r].w;
+        if (any == 0u && nr == ST_ROWS) {
+            // common case: a full stage in the middle of its rows' sums; straight-line code
+            double2 x[ST_ROWS], v01[ST_ROWS];
+#pragma unroll
+            for (int r = 0; r < ST_ROWS; ++r) {
+                x[r] = *reinterpret_cast<const double2 *>(sp + (size_t)r * rowbytes);
+                v01[r] = *reinterpret_cast<const double2 *>(hdr + 64 * r);
+            }
+#pragma unroll
+            for (int r = 0; r < ST_ROWS; ++r) {
+                acc[0].x = acc[0].x + v01[r].x * x[r].x; acc[0].y = acc[0].y + v01[r].x * x[r].y;
+                acc[1].x = acc[1].x + v01[r].y * x[r].x; acc[1].y = acc[1].y + v01[r].y * x[r].y;
                 if (NACC == 3) {
-                    const double v2 = hdr[2 * ST_ROWS + r];
-                    acc[2].x = acc[2].x + v2 * x.x; acc[2].y = acc[2].y + v2 * x.y;
+                    const double v2 = __hiloint2double(h1[r].y, h1[r].x);
+                    acc[2].x = acc[2].x + v2 * x[r].x; acc[2].y = acc[2].y + v2 * x[r].y;
                 }
-                if (fl) {                           // warp-uniform, rare
-#pragma unroll
+            }
+        } else {
+            // a sum ends in this stage (or the run does)
+#pragma unroll 1
+            for (int r = 0; r < nr; ++r) {
+                const double2 x = *reinterpret_cast<const double2 *>(sp + (size_t)r * rowbytes);
+                const double2 v01 = *reinterpret_cast<const double2 *>(hdr + 64 * r);
+                const int4 q1 = *reinterpret_cast<const int4 *>(hdr + 64 * r + 16);
+                const double v2 = __hiloint2double(q1.y, q1.x);
+                const uint32_t fl = (uint32_t)q1.w;
+                acc[0].x = acc[0].x + v01.x * x.x; acc[0].y = acc[0].y + v01.x * x.y;
+                acc[1].x = acc[1].x + v01.y * x.x; acc[1].y = acc[1].y + v01.y * x.y;
+                if (NACC == 3) { acc[2].x = acc[2].x + v2 * x.x; acc[2].y = acc[2].y + v2 * x.y; }
+                if (fl) {                           // warp-uniform
+#pragma unroll 1
                     for (int k = 0; k < NACC; ++k) {
-                        if (fl & ((SF_EVENT << k))) deliver(acc[k]);
-                        if (fl & ((SF_CLOSE << k))) acc[k] = make_double2(0.0, 0.0);
+                        if (fl & (SF_EVENT << k)) {
+                            const double2 sum = k == 0 ? acc[0] : (k == 1 ? acc[1] : acc[2]);
+                            const int2 ev = *reinterpret_cast<const int2 *>(hdr + 64 * r + 32 + 8 * k);
+                            if (ev.y < 0) {             // the row's only sum: straight to Y
+                                double *y = (ev.x < a.nrow1 ? a.Y1 + (int64_t)ev.x * a.ldy1 : a.Y2 + (int64_t)(ev.x - a.nrow1) * a.ldy2) + f0 + fo;
+                                if (active) *reinterpret_cast<double2 *>(y) = sum;
+                            } else {                    // to its partial slot; signalled later, in batches
+                                if (active) *reinterpret_cast<double2 *>(a.partials + (int64_t)ev.y * a.ldp + f0 + fo) = sum;
+                                if (lane == npend) pend = ev;
+                                if (++npend == 32) { st_flush(a, pend, npend, f0 + fo, tile * ncw + warp, a.ntile * ncw, active); npend = 0; }
+                            }
+                        }
                     }
+                    if (fl & SF_CLOSE) acc[0] = make_double2(0.0, 0.0);
+                    if (fl & (SF_CLOSE << 1)) acc[1] = make_double2(0.0, 0.0);
+                    if (fl & (SF_CLOSE << 2)) acc[2] = make_double2(0.0, 0.0);
                     if (fl & SF_SHIFT) { acc[0] = acc[1]; acc[1] = make_double2(0.0, 0.0); }
                 }
             }
@@ -502,6 +537,7 @@ __global__ void __launch_bounds__(288) spmm_stream_kernel(const StreamArgs a)
         if (lane == 0) mbar_arrive(empty + stage);
         if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
     }
+    if (npend) st_flush(a, pend, npend, f0 + fo, tile * ncw + warp, a.ntile * ncw, active);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -533,14 +569,19 @@ bool apply_stream(Weighted &M1, Weighted *M2, const double *dX, int64_t ldx, int
     const int nstage = (int)std::min<size_t>(16, budget / stagebytes);
     if (nstage < 2) return false;
     const size_t smem = 256 + (size_t)nstage * stagebytes;
-    const int R = std::max(1, sm_count() * bps / ntile);
+    // one CTA per run and field tile, ALL co-resident (a second wave would double the time): ask the occupancy
+    int occ = 0;
+    if (M2) IB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_stream_kernel<3>, 32 * (ncw + 1), smem));
+    else IB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_stream_kernel<2>, 32 * (ncw + 1), smem));
+    if (occ < 1) return false;
+    const int R = std::max(1, sm_count() * std::min(bps, occ) / ntile);
     StreamPlan &P = M1.stream_plan;
     if (!make_stream_plan(P, M1, M2, R, s)) return false;
     const int64_t ldp = (int64_t)ntile * tw;
     if (P.partials.n < (size_t)P.nslots * ldp) P.partials.alloc((size_t)P.nslots * ldp + 2, s);
     const size_t ncnt = (size_t)P.nrowS * ntile * ncw;
     if (P.counters.n != ncnt) { P.counters.alloc(ncnt, s); P.counters.zero(); }
-    StreamArgs a{P.recs.p, P.nrec, P.R, ntile, tw, nstage, P.events.p, P.run_ev0.p, P.fx_slot.p, dX, ldx, nvar, dY1, ldy1,
+    StreamArgs a{P.recs.p, P.cols.p, P.nrec, P.R, ntile, tw, nstage, P.fx_ptr.p, P.fx_slot.p, dX, ldx, nvar, dY1, ldy1,
                  (int32_t)P.nrow1, dY2, ldy2, P.partials.p, ldp, P.counters.p, P.zrows.p, (int)P.nzrows};
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(P.R * ntile));

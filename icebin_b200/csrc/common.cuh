@@ -50,7 +50,7 @@ int device_index();              // current device, < IB_MAX_DEVICES
 constexpr int IB_MAX_DEVICES = 64;
 // performance knobs (ib_tune): never change results
 struct Tune {
-    int stream_bps = 4;          // CTAs per SM of spmm_stream_kernel
+    int stream_bps = 3;          // CTAs per SM of spmm_stream_kernel
     int tma_bps = 4;             // CTAs per SM of spmm_tma_kernel
     int gc_nq = 0;               // spmm_gc_kernel: 64-field groups per lane (0: by nvar)
     int use_stream = 1;          // one-pass kernel for wide matrices

@@ -96,12 +96,12 @@ struct ApplyPlan {
 struct StreamPlan {
     bool tried = false, ok = false, fresh = true;
     uint64_t partner_uid = 0;   // uid of the stacked partner (0: none)
-    int R = 0;                  // runs (one per CTA and field tile)
+    int R = 0, R_asked = 0;     // runs (one per CTA and field tile); what the caller asked for (R <= R_asked)
     int64_t nrec = 0, nev = 0, nslots = 0, nzrows = 0, nrow1 = 0, nrowS = 0;
-    DBuf<int4> recs;            // StRec, two int4 each
-    DBuf<int4> events;          // (stacked row, partial slot or -1, first entry of the row's slot list, slots of the row)
-    DBuf<int32_t> run_ev0;      // [R+1] first event of every run
-    DBuf<uint32_t> fx_slot;     // slot lists, row by row, stream order inside a row
+    DBuf<int4> recs;            // StRec, four int4 each
+    DBuf<int32_t> cols;         // [nrec] column of every record
+    DBuf<int32_t> fx_ptr;       // [nrowS+1] slot list of every stacked row ...
+    DBuf<uint32_t> fx_slot;     // ... row by row, stream order inside a row
     DBuf<int32_t> zrows;        // rows without any entry
     DBuf<int> counters;         // completion counters [nrowS][field tile][consumer warp]; all zero between launches
     DBuf<double> partials;      // [nslots][ldp]

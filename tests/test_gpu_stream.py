@@ -14,6 +14,16 @@ def tol(M, X):
     return 1e-12 * (abs(M) @ np.abs(X)) + 1e-300
 
 
+def check(Y, M, X, what, factor=1.0, ref=None):
+    """Y == M X to the gate; on failure say where (rows / fields / how many entries)."""
+    ref = M @ X if ref is None else ref
+    bad = ~(np.abs(Y - ref) <= factor * tol(M, X))
+    if bad.any():
+        r, f = np.nonzero(bad)
+        raise AssertionError("%s: %d of %d entries off; rows %s fields %s; worst |dY| %.3e (nan: %d)" % (
+            what, bad.sum(), bad.size, np.unique(r)[:12], np.unique(f)[:12], np.nanmax(np.abs(Y - ref)), np.isnan(Y).sum()))
+
+
 def oracle_csr(Wo):
     return sp.csr_matrix((Wo.val, (Wo.row, Wo.col)), shape=Wo.shape)
 
@@ -37,14 +47,14 @@ def test_stacked_EvI_AvI_vs_oracle(mats, nvar):
     (EvI, oE), (AvI, oA) = mats["EvI"], mats["AvI"]
     X = np.random.default_rng(nvar).uniform(-1, 1, (EvI.shape[1], nvar))
     YE, YA = api.apply_many([EvI, AvI], X, layout="cell")
-    assert np.all(np.abs(YE - oE @ X) <= tol(oE, X))
-    assert np.all(np.abs(YA - oA @ X) <= tol(oA, X))
+    check(YE, oE, X, "EvI (stacked)")
+    check(YA, oA, X, "AvI (stacked)")
     # order of the matrices in the call does not matter; every call gives the same bits
     YA2, YE2 = api.apply_many([AvI, EvI], X, layout="cell")
     assert np.array_equal(YE, YE2) and np.array_equal(YA, YA2)
     # EvI alone takes the same kernel with two running sums
     Y1 = EvI.apply(X, layout="cell")
-    assert np.all(np.abs(Y1 - oE @ X) <= tol(oE, X))
+    check(Y1, oE, X, "EvI alone")
     assert np.array_equal(Y1, EvI.apply(X, layout="cell"))
 
 
@@ -106,18 +116,20 @@ def test_generic_matrices(seed, nvar):
     W2 = api.Weighted.from_csr(M2.shape[0], M2.shape[1], M2.indptr, M2.indices, M2.data)
     X = rng.uniform(-1, 1, (M1.shape[1], nvar))
     Y1, Y2 = api.apply_many([W1, W2], X, layout="cell")
-    assert np.all(np.abs(Y1 - M1 @ X) <= tol(M1, X)) and np.all(np.abs(Y2 - M2 @ X) <= tol(M2, X))
+    check(Y1, M1, X, "M1 (stacked)")
+    check(Y2, M2, X, "M2 (stacked)")
     empty1 = np.diff(M1.indptr) == 0
     assert empty1.any() and np.all(Y1[empty1] == 0.0)
     Ys = W1.apply(X, layout="cell")
-    assert np.all(np.abs(Ys - M1 @ X) <= tol(M1, X))
+    check(Ys, M1, X, "M1 alone")
     # the other kernels give the same answer to rounding
     api.tune("use_stream", 0)
     try:
         Z1, Z2 = api.apply_many([W1, W2], X, layout="cell")
     finally:
         api.tune("use_stream", 1)
-    assert np.all(np.abs(Z1 - Y1) <= 2 * tol(M1, X)) and np.all(np.abs(Z2 - Y2) <= 2 * tol(M2, X))
+    check(Z1, M1, X, "M1, other kernels vs one-pass", 2.0, Y1)
+    check(Z2, M2, X, "M2, other kernels vs one-pass", 2.0, Y2)
 
 
 def test_graph_replay_and_back_to_back(mats):
