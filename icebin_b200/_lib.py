@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libicebin_b200.so")
+# ICEBIN_B200_LIB: an instrumented build of the same sources (tools/build_trace.py); the product always loads the in-tree library
+SO_PATH = os.environ.get("ICEBIN_B200_LIB") or os.path.join(_HERE, "libicebin_b200.so")
 
 i64, i32, f64, vp, cp = C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_char_p
 PP = C.POINTER(vp)

@@ -44,7 +44,19 @@ def _newest_dep():
     return t
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None, objdir=None):
+    """defines/out/objdir: instrumented variants for tools/ (e.g. -DIB_STREAM_TRACE); the product build uses none."""
+    global OUT, OBJ
+    saved = (OUT, OBJ)
+    if out:
+        OUT, OBJ = out, objdir or (out + ".build")
+    try:
+        return _build(force, verbose, ["-D" + d for d in defines])
+    finally:
+        OUT, OBJ = saved
+
+
+def _build(force, verbose, extra):
     dep = _newest_dep()
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= dep:
         return OUT
@@ -57,7 +69,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= dep:
             return obj
-        cmd = [nvcc] + ARCH + COMMON + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + ARCH + COMMON + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

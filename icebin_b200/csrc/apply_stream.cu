@@ -218,24 +218,34 @@ struct StSlotLoad {
     }
 };
 struct StSlotEmit {
-    const int32_t *srow;
+    const int32_t *srow, *fx_ptr;
     const uint32_t *spos;           // sorted event q lives at record spos[q] / 4, accumulator spos[q] % 4
     StRec *rec;
-    uint32_t *fx_slot;
+    int2 *rowinfo;                  // (first slot, number of slots) of every row that has more than one sum
     __device__ void operator()(int64_t q, uint32_t prefix, uint32_t multi) const
     {
-        fx_slot[q] = multi ? prefix : 0xffffffffu;
+        // slots are numbered in this (row-sorted, stream order inside a row) order: a row's slots are consecutive
+        const int32_t r = srow[q];
         const uint32_t pos = spos[q];
-        rec[pos >> 2].ev[pos & 3u] = make_int2(srow[q], multi ? (int32_t)prefix : -1);
+        rec[pos >> 2].ev[pos & 3u] = make_int2(r, multi ? (int32_t)prefix : -1);
+        if (multi && q == fx_ptr[r]) rowinfo[r] = make_int2((int32_t)prefix, fx_ptr[r + 1] - fx_ptr[r]);
     }
 };
-struct StZeroLoad {
+// rows the fix-up kernel visits: more than one sum (add the slots) or none at all (zero)
+struct StFixLoad {
     const int32_t *fx_ptr;
-    __device__ uint32_t operator()(int64_t r) const { return fx_ptr[r + 1] == fx_ptr[r] ? 1u : 0u; }
+    __device__ uint32_t operator()(int64_t r) const { return fx_ptr[r + 1] - fx_ptr[r] != 1 ? 1u : 0u; }
 };
-struct StZeroEmit {
-    int32_t *zrows;
-    __device__ void operator()(int64_t r, uint32_t prefix, uint32_t z) const { if (z) zrows[prefix] = (int32_t)r; }
+struct StFixEmit {
+    const int32_t *fx_ptr;
+    int32_t *fixrows;
+    int2 *rowinfo;
+    __device__ void operator()(int64_t r, uint32_t prefix, uint32_t z) const
+    {
+        if (!z) return;
+        fixrows[prefix] = (int32_t)r;
+        if (fx_ptr[r + 1] == fx_ptr[r]) rowinfo[r] = make_int2(-1, 0);
+    }
 };
 static __global__ void st_u32_to_i32_kernel(const uint32_t *a, int64_t n, int32_t *b)
 {
@@ -301,16 +311,14 @@ static bool make_stream_plan(StreamPlan &P, Weighted &M1, Weighted *M2, int R, c
     P.nev = nev;
     P.recs.alloc((size_t)nrec * 4, s);
     P.cols.alloc((size_t)nrec, s);
-    P.fx_slot.alloc((size_t)nev + 1, s);
     if (nrec * 4 >= (int64_t(1) << 32)) return false;
     DBuf<uint32_t> er0((size_t)nev + 1, s), er1((size_t)nev + 1, s), ei0((size_t)nev + 1, s), ei1((size_t)nev + 1, s);
     scan_apply<uint32_t>(es, FL, AddU32{}, 0u, StFlagEmit{FL, vid, urec.p, reinterpret_cast<StRec *>(P.recs.p), P.cols.p, er0.p, ei0.p}, s);
     // per-row slot lists: events sorted by row, stream order inside a row (the sort is stable)
     const int w2 = radix_sort_pairs<uint32_t, uint32_t>(er0.p, ei0.p, er1.p, ei1.p, nev, bits_for(nrowS), s);
-    DBuf<int32_t> srow((size_t)nev + 1, s);
-    DBuf<int32_t> &fx_ptr = P.fx_ptr;
-    fx_ptr.alloc((size_t)nrowS + 1, s);
+    DBuf<int32_t> srow((size_t)nev + 1, s), fx_ptr((size_t)nrowS + 1, s);
     fx_ptr.zero();
+    P.rowinfo.alloc((size_t)nrowS, s);
     if (nev > 0) {
         st_u32_to_i32_kernel<<<(unsigned)cdiv(nev, 256), 256, 0, s>>>(w2 ? er1.p : er0.p, nev, srow.p);
         IB_LAUNCHED();
@@ -320,16 +328,17 @@ static bool make_stream_plan(StreamPlan &P, Weighted &M1, Weighted *M2, int R, c
     ScanState<uint32_t> ss, zs;
     transform_scan<uint32_t>(ss, nev, StSlotLoad{srow.p, fx_ptr.p}, AddU32{}, 0u, s);
     scan_apply<uint32_t>(ss, StSlotLoad{srow.p, fx_ptr.p}, AddU32{}, 0u,
-                         StSlotEmit{srow.p, w2 ? ei1.p : ei0.p, reinterpret_cast<StRec *>(P.recs.p), P.fx_slot.p}, s);
-    transform_scan<uint32_t>(zs, nrowS, StZeroLoad{fx_ptr.p}, AddU32{}, 0u, s);
-    uint32_t nslots = 0, nz = 0;
+                         StSlotEmit{srow.p, fx_ptr.p, w2 ? ei1.p : ei0.p, reinterpret_cast<StRec *>(P.recs.p), P.rowinfo.p}, s);
+    transform_scan<uint32_t>(zs, nrowS, StFixLoad{fx_ptr.p}, AddU32{}, 0u, s);
+    uint32_t nslots = 0, nfix = 0;
     IB_CUDA(cudaMemcpyAsync(&nslots, ss.total.p, sizeof nslots, cudaMemcpyDeviceToHost, s));
-    IB_CUDA(cudaMemcpyAsync(&nz, zs.total.p, sizeof nz, cudaMemcpyDeviceToHost, s));
+    IB_CUDA(cudaMemcpyAsync(&nfix, zs.total.p, sizeof nfix, cudaMemcpyDeviceToHost, s));
     IB_CUDA(cudaStreamSynchronize(s));
     P.nslots = nslots;
-    P.nzrows = nz;
-    P.zrows.alloc((size_t)nz + 1, s);
-    if (nz) scan_apply<uint32_t>(zs, StZeroLoad{fx_ptr.p}, AddU32{}, 0u, StZeroEmit{P.zrows.p}, s);
+    P.nfix = nfix;
+    P.fixrows.alloc((size_t)nfix + 1, s);
+    if (nfix) scan_apply<uint32_t>(zs, StFixLoad{fx_ptr.p}, AddU32{}, 0u, StFixEmit{fx_ptr.p, P.fixrows.p, P.rowinfo.p}, s);
+    IB_CUDA(cudaStreamSynchronize(s));      // fx_ptr and the other temporaries die here
     P.nrow1 = nrow1;
     P.nrowS = nrowS;
     P.ok = true;
@@ -337,13 +346,25 @@ static bool make_stream_plan(StreamPlan &P, Weighted &M1, Weighted *M2, int R, c
 }
 
 // ---- kernel ----------------------------------------------------------------------------------------------
+#ifdef IB_STREAM_TRACE      // tools/build_trace.py: per-CTA time stamps of the last launch (never in the product library)
+constexpr int TR_N = 8;
+__device__ unsigned long long g_stream_trace[8192 * TR_N];
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(slot) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 8192) g_stream_trace[blockIdx.x * TR_N + (slot)] = gtime(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 struct StreamArgs {
     const int4 *recs;           // StRec
     const int32_t *cols;        // column of every record (the producer needs nothing else)
     int64_t nrec;
     int R, ntile, tw, nstage;
-    const int32_t *fx_ptr;
-    const uint32_t *fx_slot;
     const double *X;
     int64_t ldx;
     int nvar;
@@ -354,58 +375,50 @@ struct StreamArgs {
     int64_t ldy2;
     double *partials;
     int64_t ldp;
-    int *counters;              // [nrowS][ntile][consumer warps]
-    const int32_t *zrows;
-    int nzrows;
 };
 
-__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-
-// Signals the partial sums a warp has stored since its last flush (lane i holds the i-th: row, slot) and finishes the rows
-// whose last slot this is.  ONE release fence and one round of atomics for the whole batch: a fence per sum stalled
-// the warp for microseconds each time (the memory system is saturated with bulk copies), this runs once or twice per
-// run.  The warp that brings a row's last slot adds the row's slots in slot order and writes Y.
-__device__ __noinline__ void st_flush(const StreamArgs &a, int2 pend, int npend, int f, int strip, int nstrip, bool active)
+// Second (small) kernel: every row with more than one sum is the sum of its slots, added in slot order (= stream
+// order, fixed at plan time); rows without any entry are zero.  One warp per (row, 64-field strip); a row's slots are
+// consecutive, so all of a row's loads are independent: one L2 round trip per row.  Launched with programmatic stream
+// serialization: the warps are resident and hold their row's (first slot, count) before the main kernel has finished.
+struct FixArgs {
+    const int32_t *fixrows;
+    const int2 *rowinfo;
+    int nfix, nstrip, nvar;
+    const double *partials;
+    int64_t ldp;
+    double *Y1;
+    int64_t ldy1;
+    int32_t nrow1;
+    double *Y2;
+    int64_t ldy2;
+};
+constexpr int FIX_WARPS = 8;
+__global__ void __launch_bounds__(FIX_WARPS * 32) spmm_stream_fixup_kernel(const FixArgs a)
 {
     const int lane = threadIdx.x & 31;
-    const bool has = lane < npend;
-    const int32_t r = has ? pend.x : 0;
-    const int fb = has ? __ldg(a.fx_ptr + r) : 0;
-    const int fn = has ? __ldg(a.fx_ptr + r + 1) - fb : 0;
-    fence_gpu();                                    // every lane's partial stores, before any lane's signal
-    __syncwarp();
-    int *cnt = a.counters + (int64_t)r * nstrip + strip;
-    const int old = has ? atomicAdd(cnt, 1) : -2;
-    const bool last = has && old == fn - 1;
-    unsigned todo = __ballot_sync(0xffffffffu, last);
-    if (todo == 0u) return;
-    fence_gpu();
-    if (last) *cnt = 0;                             // ready for the next launch
-    const double *pb = a.partials + f;
-    while (todo) {
-        const int i = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int32_t ri = __shfl_sync(0xffffffffu, r, i);
-        const int fbi = __shfl_sync(0xffffffffu, fb, i), fni = __shfl_sync(0xffffffffu, fn, i);
-        double2 t = make_double2(0.0, 0.0);
-        for (int q0 = 0; q0 < fni; q0 += 32) {
-            const int m = min(32, fni - q0);
-            const uint32_t mine = lane < m ? __ldg(a.fx_slot + fbi + q0 + lane) : 0u;
-            for (int k0 = 0; k0 < m; k0 += 4) {
-                double2 p[4];
+    const int64_t w = (int64_t)blockIdx.x * FIX_WARPS + (threadIdx.x >> 5);
+    pdl_launch_dependents();
+    const bool mine = w < (int64_t)a.nfix * a.nstrip;
+    int32_t r = 0;
+    int2 info = make_int2(-1, 0);
+    const int f = (int)(w % a.nstrip) * 64 + 2 * lane;
+    if (mine) { r = __ldg(a.fixrows + w / a.nstrip); info = __ldg(a.rowinfo + r); }      // plan data: before the wait
+    pdl_wait();
+    if (!mine || f >= a.nvar) return;
+    double2 t = make_double2(0.0, 0.0);
+    const double *pb = a.partials + (int64_t)info.x * a.ldp + f;
+    for (int q0 = 0; q0 < info.y; q0 += 8) {
+        double2 p[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t sl = __shfl_sync(0xffffffffu, mine, (k0 + u) & 31);
-                    p[u] = (k0 + u < m && active) ? __ldcg(reinterpret_cast<const double2 *>(pb + (int64_t)sl * a.ldp)) : make_double2(0.0, 0.0);
-                }
+        for (int u = 0; u < 8; ++u)
+            p[u] = q0 + u < info.y ? __ldcg(reinterpret_cast<const double2 *>(pb + (int64_t)(q0 + u) * a.ldp)) : make_double2(0.0, 0.0);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k0 + u < m) { t.x = t.x + p[u].x; t.y = t.y + p[u].y; }
-            }
-        }
-        double *y = (ri < a.nrow1 ? a.Y1 + (int64_t)ri * a.ldy1 : a.Y2 + (int64_t)(ri - a.nrow1) * a.ldy2) + f;
-        if (active) *reinterpret_cast<double2 *>(y) = t;
+        for (int u = 0; u < 8; ++u)
+            if (q0 + u < info.y) { t.x = t.x + p[u].x; t.y = t.y + p[u].y; }
     }
+    double *y = (r < a.nrow1 ? a.Y1 + (int64_t)r * a.ldy1 : a.Y2 + (int64_t)(r - a.nrow1) * a.ldy2) + f;
+    *reinterpret_cast<double2 *>(y) = t;
 }
 
 template <int NACC>
@@ -420,6 +433,7 @@ __global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = (int)(blockDim.x >> 5) - 1;     // consumer warps
     pdl_launch_dependents();
+    if (warp == 0) TRACE(0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, ncw); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -436,6 +450,7 @@ __global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_consta
         const uint32_t tb = (uint32_t)live * 8u;
         int c_next = (lane < ST_ROWS && jb + lane < je) ? __ldg(a.cols + jb + lane) : 0;
         pdl_wait();                                 // X may be the previous kernel's output
+        TRACE(1);
         for (int j = jb; j < je; j += ST_ROWS) {
             const int nr = min(ST_ROWS, je - j);
             const int c = c_next;
@@ -451,26 +466,20 @@ __global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_consta
             else if (lane == ST_ROWS) bulk_g2s(sp + (size_t)ST_ROWS * rowbytes, a.recs + 4 * (int64_t)j, 64u * (uint32_t)nr, full + stage);
             if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
         }
+        TRACE(5);
         return;
     }
     // ===== consumer warps: lane owns fields f0 + 64*warp + 2*lane, +1
     const int fo = 64 * warp + 2 * lane;            // offset inside the tile (< tw: always inside the row buffer)
     const bool active = fo < live;
     pdl_wait();                                     // nothing is written before the previous kernel has completed
-    // rows without any entry are zero
-    for (int z = run; z < a.nzrows; z += a.R) {       // every consumer warp zeroes its own strip of the row
-        const int32_t r = __ldg(a.zrows + z);
-        double *y = r < a.nrow1 ? a.Y1 + (int64_t)r * a.ldy1 : a.Y2 + (int64_t)(r - a.nrow1) * a.ldy2;
-        if (active) *reinterpret_cast<double2 *>(y + f0 + fo) = make_double2(0.0, 0.0);
-    }
     double2 acc[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) acc[k] = make_double2(0.0, 0.0);
-    int2 pend = make_int2(0, 0);                    // lane i: the i-th partial sum stored since the last flush
-    int npend = 0;
     for (int j = jb; j < je; j += ST_ROWS) {
         const int nr = min(ST_ROWS, je - j);
         mbar_wait(full + stage, phase);
+        if (warp == 0 && j == jb) TRACE(2);
         const unsigned char *sb = data + (size_t)stage * stagebytes;
         const unsigned char *hdr = sb + (size_t)ST_ROWS * rowbytes;
         const unsigned char *sp = sb + (size_t)fo * 8;
@@ -516,14 +525,10 @@ __global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_consta
                         if (fl & (SF_EVENT << k)) {
                             const double2 sum = k == 0 ? acc[0] : (k == 1 ? acc[1] : acc[2]);
                             const int2 ev = *reinterpret_cast<const int2 *>(hdr + 64 * r + 32 + 8 * k);
-                            if (ev.y < 0) {             // the row's only sum: straight to Y
-                                double *y = (ev.x < a.nrow1 ? a.Y1 + (int64_t)ev.x * a.ldy1 : a.Y2 + (int64_t)(ev.x - a.nrow1) * a.ldy2) + f0 + fo;
-                                if (active) *reinterpret_cast<double2 *>(y) = sum;
-                            } else {                    // to its partial slot; signalled later, in batches
-                                if (active) *reinterpret_cast<double2 *>(a.partials + (int64_t)ev.y * a.ldp + f0 + fo) = sum;
-                                if (lane == npend) pend = ev;
-                                if (++npend == 32) { st_flush(a, pend, npend, f0 + fo, tile * ncw + warp, a.ntile * ncw, active); npend = 0; }
-                            }
+                            // the row's only sum goes straight to Y, any other to its slot (added up by the fix-up kernel)
+                            double *dst = ev.y >= 0 ? a.partials + (int64_t)ev.y * a.ldp
+                                                    : (ev.x < a.nrow1 ? a.Y1 + (int64_t)ev.x * a.ldy1 : a.Y2 + (int64_t)(ev.x - a.nrow1) * a.ldy2);
+                            if (active) *reinterpret_cast<double2 *>(dst + f0 + fo) = sum;
                         }
                     }
                     if (fl & SF_CLOSE) acc[0] = make_double2(0.0, 0.0);
@@ -537,7 +542,7 @@ __global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_consta
         if (lane == 0) mbar_arrive(empty + stage);
         if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
     }
-    if (npend) st_flush(a, pend, npend, f0 + fo, tile * ncw + warp, a.ntile * ncw, active);
+    if (warp == 0) { TRACE(3); TRACE(4); }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -579,27 +584,43 @@ bool apply_stream(Weighted &M1, Weighted *M2, const double *dX, int64_t ldx, int
     if (!make_stream_plan(P, M1, M2, R, s)) return false;
     const int64_t ldp = (int64_t)ntile * tw;
     if (P.partials.n < (size_t)P.nslots * ldp) P.partials.alloc((size_t)P.nslots * ldp + 2, s);
-    const size_t ncnt = (size_t)P.nrowS * ntile * ncw;
-    if (P.counters.n != ncnt) { P.counters.alloc(ncnt, s); P.counters.zero(); }
-    StreamArgs a{P.recs.p, P.cols.p, P.nrec, P.R, ntile, tw, nstage, P.fx_ptr.p, P.fx_slot.p, dX, ldx, nvar, dY1, ldy1,
-                 (int32_t)P.nrow1, dY2, ldy2, P.partials.p, ldp, P.counters.p, P.zrows.p, (int)P.nzrows};
+    StreamArgs a{P.recs.p, P.cols.p, P.nrec, P.R, ntile, tw, nstage, dX, ldx, nvar, dY1, ldy1,
+                 (int32_t)P.nrow1, dY2, ldy2, P.partials.p, ldp};
+    // programmatic stream serialization: the prologue of a kernel overlaps the tail of the one before it
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(P.R * ntile));
     cfg.blockDim = dim3((unsigned)(32 * (ncw + 1)));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    // programmatic stream serialization: the prologue overlaps the previous kernel's tail.  The first launch after
-    // the plan was built is an ordinary one (the kernel reads plan data before griddepcontrol.wait).
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = P.fresh ? 0 : 1;
-    P.fresh = false;
+    cfg.numAttrs = 1;
     if (M2) IB_CUDA(cudaLaunchKernelEx(&cfg, spmm_stream_kernel<3>, a));
     else IB_CUDA(cudaLaunchKernelEx(&cfg, spmm_stream_kernel<2>, a));
     IB_LAUNCHED();
+    if (P.nfix > 0) {
+        const int nstrip = (nvar + 63) / 64;
+        FixArgs fa{P.fixrows.p, P.rowinfo.p, (int)P.nfix, nstrip, nvar, P.partials.p, ldp, dY1, ldy1, (int32_t)P.nrow1, dY2, ldy2};
+        cudaLaunchConfig_t fc{};
+        fc.gridDim = dim3((unsigned)cdiv(P.nfix * nstrip, FIX_WARPS));
+        fc.blockDim = dim3(FIX_WARPS * 32);
+        fc.stream = s;
+        fc.attrs = attr;
+        fc.numAttrs = 1;
+        IB_CUDA(cudaLaunchKernelEx(&fc, spmm_stream_fixup_kernel, fa));
+        IB_LAUNCHED();
+    }
     return true;
 }
+
+#ifdef IB_STREAM_TRACE
+extern "C" int ib_debug_stream_trace(unsigned long long *out, int nblk)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_stream_trace, sizeof(unsigned long long) * TR_N * nblk);
+}
+#endif
 
 }   // namespace ib

@@ -94,16 +94,14 @@ struct ApplyPlan {
 
 // One-pass plan for wide matrices, alone or stacked with a partner that shares the input space (apply_stream.cu)
 struct StreamPlan {
-    bool tried = false, ok = false, fresh = true;
+    bool tried = false, ok = false;
     uint64_t partner_uid = 0;   // uid of the stacked partner (0: none)
     int R = 0, R_asked = 0;     // runs (one per CTA and field tile); what the caller asked for (R <= R_asked)
-    int64_t nrec = 0, nev = 0, nslots = 0, nzrows = 0, nrow1 = 0, nrowS = 0;
+    int64_t nrec = 0, nev = 0, nslots = 0, nfix = 0, nrow1 = 0, nrowS = 0;
     DBuf<int4> recs;            // StRec, four int4 each
     DBuf<int32_t> cols;         // [nrec] column of every record
-    DBuf<int32_t> fx_ptr;       // [nrowS+1] slot list of every stacked row ...
-    DBuf<uint32_t> fx_slot;     // ... row by row, stream order inside a row
-    DBuf<int32_t> zrows;        // rows without any entry
-    DBuf<int> counters;         // completion counters [nrowS][field tile][consumer warp]; all zero between launches
+    DBuf<int2> rowinfo;         // [nrowS] (first partial slot, slots) of rows with several sums; (-1, 0) = no entry at all
+    DBuf<int32_t> fixrows;      // [nfix] the rows the fix-up kernel visits
     DBuf<double> partials;      // [nslots][ldp]
 };
 
