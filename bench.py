@@ -6,9 +6,13 @@
 Workload (config.workload): BASELINE.json configs[2] on the configs[1] grids -- ModelE 2x2.5 (144x90) A grid +
 SeaRISE-shaped Greenland 5 km ice grid (301x561), 40 elevation classes; one STEP pushes a batch of 512 fp64 fields
 defined on the ice grid through EvI and AvI (scale=true, correctA=true), i.e. the I->E and I->A half of a coupling
-step (IceCoupler.cpp:445-446).  value = (nnz(EvI)+nnz(AvI)) * nvar / time, in Gnnz/s, whole job.
-With N>1 (torchrun, one rank per GPU) every rank owns one ice sheet (weak scaling) and the sheets' A-/E-grid
-contributions are merged with an NCCL all-reduce (multivec.cpp:35-81); see DESIGN.md.
+step (IceCoupler.cpp:445-446), as ONE call of ib_w_apply_many_dev.  value = (nnz(EvI)+nnz(AvI)) * nvar / time, in
+Gnnz/s, whole job.  With N>1 (torchrun, one rank per GPU) every rank owns one ice sheet (weak scaling) and the
+sheets' A-/E-grid contributions are merged across ranks (multivec.cpp:35-81); see DESIGN.md.
+
+The same line also carries the rest of BASELINE.json's metric, measured in the same run (`more`): six-matrix build
+times (5 km and Greenland 1 km), the other applies (IvE, IvA, sigma-smoothed IvE), first-apply (plan) costs, a
+coupler-shaped step (rebuild + 26 fields), Hntr at ETOPO1 scale; at N>1 the strong-scaling build of configs[4].
 
 Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference (oracle/, single
 thread: the reference is serial) on the same workload.
@@ -26,10 +30,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one EvI spmm_tma_kernel launch at the default workload
-# (ncu --set full capture, profiles/r1_spmm_tma_full_raw.csv): 284.70 MB + 22.02 MB
-NCU_TRAFFIC_EVI = 306718464
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at the default workload, from the
+# committed `ncu --set full` capture (see profiles/README.md); None until captured for the current kernel
+NCU_TRAFFIC = {"kernel": "spmm_stream_kernel<3>", "bytes": None, "source": None}
+try:
+    _t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    NCU_TRAFFIC = _t
+except Exception:
+    pass
 
 
 def parse():
@@ -43,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="kernel experiments only; the driver never passes this")
+    ap.add_argument("--no-more", action="store_true", help="skip the secondary measurements (`more`)")
     return ap.parse_args()
 
 
@@ -56,13 +65,19 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def gridA_global():
+    from icebin_b200 import synth
+    im, jm = 144, 90
+    ids = np.arange(im * jm, dtype=np.int64)
+    return synth.GridA(im, jm, im * jm, ids, (synth.A_W * synth.A_H) * (1.0 + 0.08 * np.sin(0.37 * (ids % im) + 0.21 * (ids // im))))
+
+
 def make_config(shape, rank=0):
     """Per-rank sheet: same shape, different seed and anchor so that neighbouring ranks share boundary A cells."""
     from icebin_b200 import synth
     hc = synth.hcdefs_conserv(40)
-    im, jm = 144, 90
-    ids = np.arange(im * jm, dtype=np.int64)
-    gA = synth.GridA(im, jm, im * jm, ids, (synth.A_W * synth.A_H) * (1.0 + 0.08 * np.sin(0.37 * (ids % im) + 0.21 * (ids // im))))
+    gA = gridA_global()
+    im = gA.im
     nx, ny, dx = synth.SHEET_SHAPES[shape]
     npx = int(np.ceil(nx * dx * 1e3 / synth.A_W)) + 1
     shift = max(1, int(0.62 * npx))          # neighbouring sheets' ice overlaps in a few columns of A cells
@@ -169,6 +184,197 @@ def workload_config(args, shE, shA, nnzE, nnzA):
             "parallelism": "1 ice sheet per GPU" if args.gpus > 1 else "single GPU"}
 
 
+# ---------------------------------------------------------------------------------------------------------------
+def ev_time(torch, fn, n, warm=3):
+    """Average device time of fn() over n back-to-back calls (CUDA events on the current stream), ms."""
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def timed_build(torch, gcm, name, em, specs, reps, **kw):
+    ts = []
+    for it in range(reps + 2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rm = gcm.regrid_matrices(name, em, **kw)
+        mats = {s: rm.matrix(s) for s in specs}
+        torch.cuda.synchronize()
+        if it >= 2:
+            ts.append(1e3 * (time.perf_counter() - t0))
+        del mats, rm
+    return statistics.median(ts), min(ts)
+
+
+SIX = ("EvI", "AvI", "IvE", "IvA", "EvA", "AvE")
+
+
+def more_single_gpu(torch, api, args, cfg, gcm, mats, X, YE, YA, stream, peak, nrep):
+    """The rest of BASELINE.json's metric on one GPU.  Every entry is guarded: a failure is recorded, never fatal."""
+    from icebin_b200 import synth
+    dev = X.device
+    nvar = args.nvar
+    sh, em = cfg["sheets"][0], cfg["elevmask"][0]
+    out = {}
+
+    def guarded(key, fn):
+        try:
+            out[key] = fn()
+        except Exception as e:      # never let a side measurement break the contract line
+            out[key] = {"error": str(e).splitlines()[0][:200]}
+            sys.stderr.write("bench.py: %s not measured (%s)\n" % (key, out[key]["error"]))
+
+    def apply_stats(M, ms, x_once_rows=None):
+        alg = 12 * M.nnz + 4 * (M.shape[0] + 1) + 8 * nvar * (M.shape[0] + M.shape[1])
+        return {"shape": list(M.shape), "nnz": M.nnz, "ms": ms, "Gnnz_s": M.nnz * nvar / ms / 1e6, "algorithmic_bytes": alg,
+                "alg_GBs": alg / ms / 1e6, "frac_of_peak": alg / ms / 1e6 / peak}
+
+    # ---- the other applies of the matrix set, each alone
+    def applies():
+        res = {}
+        YI = torch.empty((mats["IvE"].shape[0], nvar), dtype=torch.float64, device=dev)
+        for name, Xin, Yout in (("EvI", X, YE), ("AvI", X, YA), ("IvE", YE, YI), ("IvA", YA, YI)):
+            M = mats[name]
+            ms = ev_time(torch, lambda: M.apply_dev(Xin.data_ptr(), nvar, nvar, Yout.data_ptr(), nvar, True, stream), nrep)
+            res[name] = apply_stats(M, ms)
+        # configs[2] "with sigma smoothing enabled": the smoothed IvE, conservation correction included
+        rms = gcm.regrid_matrices(sh.name, em, scale=True, correctA=True, sigma=(50e3, 50e3, 100.0))
+        t0 = time.perf_counter()
+        IvEs = rms.matrix("IvE")
+        torch.cuda.synchronize()
+        bms = 1e3 * (time.perf_counter() - t0)
+        ms = ev_time(torch, lambda: IvEs.apply_dev(YE.data_ptr(), nvar, nvar, YI.data_ptr(), nvar, True, stream), max(3, nrep // 4))
+        res["IvE_smoothed"] = dict(apply_stats(IvEs, ms), sigma=[50e3, 50e3, 100.0], build_ms=bms, force_conservation=True)
+        return res
+    guarded("applies_alone", applies)
+
+    # ---- first-apply cost (plan construction) per matrix: first call minus a steady-state call, fresh matrices
+    def plans():
+        rm = gcm.regrid_matrices(sh.name, em, scale=True, correctA=True)
+        res = {}
+        YI = torch.empty((mats["IvE"].shape[0], nvar), dtype=torch.float64, device=dev)
+        for name, Xin, Yout in (("EvI+AvI", X, None), ("IvE", YE, YI), ("IvA", YA, YI)):
+            if name == "EvI+AvI":
+                Ms = [rm.matrix("EvI"), rm.matrix("AvI")]
+                fn = lambda: api.apply_many_dev(Ms, X.data_ptr(), nvar, nvar, [YE.data_ptr(), YA.data_ptr()], [nvar, nvar], True, stream)
+            else:
+                M = rm.matrix(name)
+                fn = lambda: M.apply_dev(Xin.data_ptr(), nvar, nvar, Yout.data_ptr(), nvar, True, stream)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); t1 = time.perf_counter()
+            fn(); torch.cuda.synchronize(); t2 = time.perf_counter()
+            res[name] = {"first_apply_ms": 1e3 * (t1 - t0), "next_apply_ms": 1e3 * (t2 - t1), "plan_ms": 1e3 * ((t1 - t0) - (t2 - t1))}
+        return res
+    guarded("plan_ms", plans)
+
+    # ---- a coupler-shaped step (IceCoupler.cpp:361-468): rebuild E1vI / A1vI (unscaled, correctA) and the smoothless IvE,
+    # apply EvI and AvI once to 26 fields and IvE once to 5 -- matrices used once, so plan cost is inside
+    def coupler():
+        nf_out, nf_in = 26, 5
+        Xc = torch.rand((X.shape[0], nf_out), dtype=torch.float64, device=dev)
+        Yc = [torch.empty((YE.shape[0], nf_out), dtype=torch.float64, device=dev), torch.empty((YA.shape[0], nf_out), dtype=torch.float64, device=dev)]
+        Zc = torch.rand((YE.shape[0], nf_in), dtype=torch.float64, device=dev)
+        Ic = torch.empty((X.shape[0], nf_in), dtype=torch.float64, device=dev)
+        ts = []
+        for it in range(7):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rm = gcm.regrid_matrices(sh.name, em, scale=False, correctA=True)
+            E, A = rm.matrix("EvI"), rm.matrix("AvI")
+            I = gcm.regrid_matrices(sh.name, em, scale=True, correctA=True).matrix("IvE")
+            api.apply_many_dev([E, A], Xc.data_ptr(), nf_out, nf_out, [y.data_ptr() for y in Yc], [nf_out, nf_out], True, stream)
+            I.apply_dev(Zc.data_ptr(), nf_in, nf_in, Ic.data_ptr(), nf_in, True, stream)
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(1e3 * (time.perf_counter() - t0))
+        return {"ms_median": statistics.median(ts), "min": min(ts),
+                "what": "regrid_matrices x2 + matrix(EvI, AvI unscaled; IvE) + apply_many([EvI, AvI]) on 26 fields + IvE on 5 fields, wall clock, host elevmask upload included"}
+    guarded("coupler_shaped_step", coupler)
+
+    # ---- north-star build target: Greenland 1 km x 40 ECs, six matrices
+    def build_1km():
+        gA = gridA_global()
+        _, gr = synth.make_gcm_and_sheet("greenland_1km", anchor=(40, 60), gridA=gA, name="greenland_1km")
+        em1 = synth.make_elevmask(gr, cfg["hcdefs"][-1], 0)
+        g1 = api.GCMRegridder(gA, cfg["hcdefs"], True)
+        g1.add_sheet(gr.name, gr)
+        med, mn = timed_build(torch, g1, gr.name, em1, SIX, 5, scale=True, correctA=True)
+        return {"six_matrices_median_ms": med, "min_ms": mn, "nI": gr.nI, "nX": gr.nX, "target_ms": 100.0,
+                "what": "regrid_matrices + matrix() x {EvI,AvI,IvE,IvA,EvA,AvE}, scale+correctA, wall clock, host elevmask upload (34 MB) included"}
+    guarded("build_greenland_1km", build_1km)
+
+    # ---- Hntr at ETOPO1 scale (make_topoo / etopo1_ice.cpp:17-29): 21600x10800 -> 144x90 and 360x180
+    def hntr():
+        res = {}
+        G = api.GRIDS
+        A = G["g1mx1m"]
+        src16 = torch.randint(-500, 4000, (A.size,), dtype=torch.int16, device=dev)
+        for bname in ("g2hx2", "g1x1"):
+            h = api.Hntr(17.17, G[bname], A, 0.0)
+            o = torch.empty(G[bname].size, dtype=torch.float64, device=dev)
+            ms = ev_time(torch, lambda: h.regrid_dev(0, src16.data_ptr(), 1, o.data_ptr(), True, 1.0, 0.0, stream), 20)
+            byt = 2 * A.size + 8 * G[bname].size
+            res["g1mx1m->%s int16, constant weight" % bname] = {"ms": ms, "algorithmic_bytes": byt, "alg_GBs": byt / ms / 1e6, "frac_of_peak": byt / ms / 1e6 / peak}
+        del src16
+        src64 = torch.rand(A.size, dtype=torch.float64, device=dev)
+        w64 = (torch.rand(A.size, device=dev) < 0.3).to(torch.float64)
+        for bname in ("g2hx2", "g1x1"):
+            h = api.Hntr(17.17, G[bname], A, 0.0)
+            o = torch.empty(G[bname].size, dtype=torch.float64, device=dev)
+            ms = ev_time(torch, lambda: h.regrid_dev(w64.data_ptr(), src64.data_ptr(), 0, o.data_ptr(), True, 1.0, 0.0, stream), 10)
+            byt = 16 * A.size + 8 * G[bname].size
+            res["g1mx1m->%s fp64, fp64 weights" % bname] = {"ms": ms, "algorithmic_bytes": byt, "alg_GBs": byt / ms / 1e6, "frac_of_peak": byt / ms / 1e6 / peak}
+        return res
+    guarded("hntr_etopo1", hntr)
+    return out
+
+
+def strong_scaling_build(torch, dist, api, args, world, rank, dev):
+    """configs[4] at N GPUs: the GCM cells of each 1 km sheet are cut into N domains of equal exchange-cell count
+    (multi.partition_cellsA -> GCMRegridder.filter_cellsA, the reference's chunking: modele/global_ec.cpp:818-893); every
+    rank builds the six matrices of its domain; the job's time is the slowest rank's median."""
+    from icebin_b200 import multi, synth
+    hc = synth.hcdefs_conserv(40)
+    gA = gridA_global()
+    out = {}
+    shapes = [("greenland_1km", (40, 60), 5)]
+    try:
+        import psutil
+        per_rank = psutil.virtual_memory().available / max(1, world)
+    except Exception:
+        per_rank = 0
+    if per_rank > 24e9:
+        shapes.append(("antarctica_1km", (40, 2), 3))
+    else:
+        out["antarctica_1km"] = {"skipped": "less than 24 GB of host memory per rank for the synthetic 36 M-cell grid"}
+    for shape, anchor, reps in shapes:
+        _, sh = synth.make_gcm_and_sheet(shape, anchor=anchor, gridA=gA, name=shape)
+        em = synth.make_elevmask(sh, hc[-1], 0)
+        g = api.GCMRegridder(gA, hc, True)
+        g.add_sheet(sh.name, sh)
+        nX_full = g.nX(sh.name)
+        if world > 1:
+            g.filter_cellsA(multi.partition_cellsA(sh.ex_ij[:, 0], gA.nA, world)[rank])
+        nX_mine = g.nX(sh.name)
+        del sh
+        if world > 1:
+            dist.barrier()
+        med, mn = timed_build(torch, g, shape, em, SIX, reps, scale=False, correctA=True)
+        t = torch.tensor([med, float(nX_mine)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[shape] = {"six_matrices_ms_slowest_rank_median": float(t[0].item()), "nX": nX_full, "nX_largest_domain": int(t[1].item()), "ranks": world}
+        del g, em
+    out["what"] = "strong scaling: every rank builds {EvI,AvI,IvE,IvA,EvA,AvE} (unscaled, correctA) for its GCM-cell domain of the sheet; rows of AvI/EvI of the domains are disjoint and concatenate (ib_w_combine_chunks)"
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -191,28 +397,22 @@ def run_b200(args):
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
+    peak, peak_src = measured_peak()
 
     cfg = make_config(args.shape, rank)
     sh = cfg["sheets"][0]
     gcm = api.GCMRegridder(cfg["gridA"], cfg["hcdefs"], True)
     gcm.add_sheet(sh.name, sh)
 
-    # ---- regrid-matrix build (six matrices, scale+correctA), device-resident inputs
+    # ---- regrid-matrix build (six matrices, scale+correctA) on the headline grids
     em_host = cfg["elevmask"][0]
-    build_ms = []
-    for it in range(8):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        rm = gcm.regrid_matrices(sh.name, em_host, scale=True, correctA=True)
-        mats = {s: rm.matrix(s) for s in ("EvI", "AvI", "IvE", "IvA", "EvA", "AvE")}
-        torch.cuda.synchronize()
-        if it >= 3:
-            build_ms.append(1e3 * (time.perf_counter() - t0))
-    build_med = statistics.median(build_ms)
+    build_med, build_min = timed_build(torch, gcm, sh.name, em_host, SIX, 5, scale=True, correctA=True)
     if world > 1:           # whole-job build time = slowest rank (every rank builds the matrices of its own sheet)
         tb = torch.tensor([build_med], dtype=torch.float64, device=dev)
         dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         build_med = float(tb.item())
+    rm = gcm.regrid_matrices(sh.name, em_host, scale=True, correctA=True)
+    mats = {s: rm.matrix(s) for s in SIX}
     EvI, AvI = mats["EvI"], mats["AvI"]
     nvar = args.nvar
     nI_d, nE_d, nA_d = EvI.shape[1], EvI.shape[0], AvI.shape[0]
@@ -243,7 +443,7 @@ def run_b200(args):
         merge_done = [torch.cuda.Event() for _ in range(2)]
 
     YE_p, YA_p = YE.data_ptr(), YA.data_ptr()
-    # pre-built argument arrays for the C ABI (the per-step Python cost matters at a 110 us step)
+    # pre-built argument arrays for the C ABI (the per-step Python cost matters at a 60 us step)
     import ctypes as C
     from icebin_b200._lib import vp as _vp
     _W2 = (_vp * 2)(EvI._h, AvI._h)
@@ -257,8 +457,8 @@ def run_b200(args):
     fresh = [True, True]       # no exchange pending on buffer set k (start of the run / of a captured graph)
 
     def step():
-        # EvI and AvI act on the same ice-grid fields (IceCoupler.cpp:445-446): one batched call, the two independent
-        # SpMMs run concurrently on forked streams and join back on `stream`
+        # EvI and AvI act on the same ice-grid fields (IceCoupler.cpp:445-446): one call; the library applies the
+        # stacked [EvI; AvI] in one pass over X (spmm_stream_kernel<3> + its small fix-up kernel)
         if mergeA is None:
             check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[0], _ld2, 1, _st))
             return
@@ -269,10 +469,9 @@ def run_b200(args):
         fresh[k] = False
         check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[k], _ld2, 1, _st))
         spmm_done[k].record(tstream)
-        with torch.cuda.stream(side):
-            side.wait_event(spmm_done[k])
-            merges[k].run([YEs[k], YAs[k]], side.cuda_stream)
-            merge_done[k].record(side)
+        side.wait_event(spmm_done[k])
+        merges[k].run([YEs[k], YAs[k]], side)
+        merge_done[k].record(side)
 
     def drain():
         if mergeA is not None:
@@ -289,12 +488,12 @@ def run_b200(args):
     drain()
     torch.cuda.synchronize()
 
-    # CUDA graph of GSTEPS consecutive steps (launch-bound otherwise: ~10 launches + a collective per 110 us step).
-    # The library's forked streams, its stream-ordered allocations and the NCCL all-reduce are all capturable.
+    # CUDA graph of GSTEPS consecutive steps (launch-bound otherwise).  The library's launches (programmatic dependent
+    # launches included) and its stream-ordered allocations are capturable.
     GSTEPS = 8
     graph, launches_per_graph = None, None
     # single-GPU only: with NCCL inside the capture one rank falling back to eager while another replays would
-    # desynchronise the collectives, and the few percent it buys at N>1 are not worth that risk
+    # desynchronise the collectives
     if not args.no_graph and args.steps >= GSTEPS and world == 1:
         try:
             torch.cuda.synchronize()
@@ -313,7 +512,6 @@ def run_b200(args):
             graph = None
             torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -348,105 +546,119 @@ def run_b200(args):
         nnz_total = float(tn.item())
     else:
         nnz_total = float(nnz)
-    # ---- roofline of the dominant kernel: the EvI apply alone, bracketed by events, same number of steps
+    # ---- roofline of the dominant kernel (spmm_stream_kernel<3>, the stacked apply), alone: an event pair around every
+    # apply, same number of steps, right after the timed region (inside the N>1 step it overlaps the exchange)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         kev[i][0].record()
-        EvI.apply_dev(X.data_ptr(), nvar, nvar, YE_p, nvar, True, stream)
+        check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[0], _ld2, 1, _st))
         kev[i][1].record()
     torch.cuda.synchronize()
     sampler.stop_flag = True
-    kms = [a.elapsed_time(b) for a, b in kev]
-    evi_ms = statistics.mean(kms)
+    stack_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
 
-    # ---- the I-side applies of the same matrix set (north star: "batched AvI/EvI/IvE application"), each alone, CUDA
-    # events around a loop of applies; reported beside the headline, not part of it
-    other = None
-    if world == 1 and not args.no_e2e:
+    nrep_side = max(3, min(args.steps, 100))
+    more = None
+    if world == 1 and not args.no_more:
+        more = more_single_gpu(torch, api, args, cfg, gcm, mats, X, YE, YA, stream, peak, nrep_side)
+    if world > 1 and not args.no_more:
         try:
-            other = {}
-            peak_o, _ = measured_peak()
-            YI = torch.empty((nI_d, nvar), dtype=torch.float64, device=dev)
-            for name, Xin in (("IvE", YE), ("IvA", YA)):
-                M = mats[name]
-                assert M.shape == (nI_d, Xin.shape[0])
-                for _ in range(3):
-                    M.apply_dev(Xin.data_ptr(), nvar, nvar, YI.data_ptr(), nvar, True, stream)
-                oe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                nrep = max(3, min(args.steps, 100))
-                oe[0].record()
-                for _ in range(nrep):
-                    M.apply_dev(Xin.data_ptr(), nvar, nvar, YI.data_ptr(), nvar, True, stream)
-                oe[1].record()
-                torch.cuda.synchronize()
-                oms = oe[0].elapsed_time(oe[1]) / nrep
-                oalg = 12 * M.nnz + 4 * (M.shape[0] + 1) + 8 * nvar * (M.shape[0] + M.shape[1])
-                other[name] = {"shape": list(M.shape), "nnz": M.nnz, "ms": oms, "Gnnz_s": M.nnz * nvar / oms / 1e6,
-                               "alg_GBs": oalg / oms / 1e6, "frac_of_peak": oalg / oms / 1e6 / peak_o}
-            del YI
-        except Exception as e:      # never let the side measurement break the contract line
-            sys.stderr.write("bench.py: I-side applies not measured (%s)\n" % str(e).splitlines()[0])
-            other = None
+            more = {"build_config5_strong_scaling": strong_scaling_build(torch, dist, api, args, world, rank, dev)}
+        except Exception as e:
+            more = {"build_config5_strong_scaling": {"error": str(e).splitlines()[0][:200]}}
 
-    # ---- e2e: the reference-facing host-buffer call (ib_w_apply), H2D of X and D2H of Y inside the timed region
+    # ---- e2e: the reference-facing host-buffer call, H2D of X and D2H of both results inside the timed region
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if not args.no_e2e:
         Xh = torch.empty((nI_d, nvar), dtype=torch.float64, pin_memory=True)
         Xh.copy_(X.cpu())
         YEh = torch.empty((nE_d, nvar), dtype=torch.float64, pin_memory=True)
         YAh = torch.empty((nA_d, nvar), dtype=torch.float64, pin_memory=True)
         L = lib()
-
-        import ctypes as C
         Wp = (C.c_void_p * 2)(EvI._h, AvI._h)
-        Yp = (C.c_void_p * 2)(YEh.data_ptr(), YAh.data_ptr())
-        ldp = (C.c_int64 * 2)(nvar, nvar)
-
-        def e2e_step():
-            check(L.ib_w_apply_many(2, Wp, Xh.data_ptr(), nvar, nvar, Yp, ldp, 0, 1))
-        for _ in range(2):
-            e2e_step()
         ne = max(3, min(args.steps, 20))
-        t0 = time.perf_counter()
-        for _ in range(ne):
-            e2e_step()
-        te = (time.perf_counter() - t0) / ne
-        e2e = {"value": nnz * nvar / te / 1e9, "unit": "Gnnz/s", "ms_per_step": 1e3 * te,
-               "h2d_bytes_per_step": nI_d * nvar * 8, "d2h_bytes_per_step": (nE_d + nA_d) * nvar * 8,
-               "api": "ib_w_apply_many([EvI, AvI]) with pinned host buffers: X uploaded once, both results downloaded"}
-        assert torch.equal(YEh.to(dev), YE), "e2e result differs from the device-resident result"
+        if world == 1:
+            def timed(fn):
+                for _ in range(2):
+                    fn()
+                t0 = time.perf_counter()
+                for _ in range(ne):
+                    fn()
+                return (time.perf_counter() - t0) / ne
+            Yp = (C.c_void_p * 2)(YEh.data_ptr(), YAh.data_ptr())
+            ldp = (C.c_int64 * 2)(nvar, nvar)
+            te = timed(lambda: check(L.ib_w_apply_many(2, Wp, Xh.data_ptr(), nvar, nvar, Yp, ldp, 0, 1)))
+            assert torch.allclose(YEh.to(dev), YE, rtol=1e-11, atol=1e-12), "e2e result differs from the device-resident result"
+            # the reference's own layout, [nvar x ncell] (IceCoupler.cpp:231-233): one device transposition each way
+            Xf = torch.empty((nvar, nI_d), dtype=torch.float64, pin_memory=True)
+            Xf.copy_(X.t().cpu())
+            YEf = torch.empty((nvar, nE_d), dtype=torch.float64, pin_memory=True)
+            YAf = torch.empty((nvar, nA_d), dtype=torch.float64, pin_memory=True)
+            Ypf = (C.c_void_p * 2)(YEf.data_ptr(), YAf.data_ptr())
+            ldf = (C.c_int64 * 2)(nE_d, nA_d)
+            tf = timed(lambda: check(L.ib_w_apply_many(2, Wp, Xf.data_ptr(), nI_d, nvar, Ypf, ldf, 1, 1)))
+            assert torch.equal(YEf.t().contiguous(), YEh), "field-major e2e result differs from the cell-major one"
+            e2e = {"value": nnz * nvar / te / 1e9, "unit": "Gnnz/s", "ms_per_step": 1e3 * te,
+                   "h2d_bytes_per_step": nI_d * nvar * 8, "d2h_bytes_per_step": (nE_d + nA_d) * nvar * 8,
+                   "api": "ib_w_apply_many([EvI, AvI]) with pinned host buffers, cell-major fields: X uploaded once, both results downloaded",
+                   "field_major": {"value": nnz * nvar / tf / 1e9, "ms_per_step": 1e3 * tf,
+                                   "note": "the reference's [nvar x ncell] layout (IB_LAYOUT_FIELD_MAJOR): transposed on the device both ways"}}
+        else:
+            # every rank: upload its sheet's fields, apply, merge across ranks, download -- wall clock, barrier on both sides
+            def e2e_step():
+                X.copy_(Xh, non_blocking=True)
+                check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[0], _ld2, 1, _st))
+                merges[0].run([YEs[0], YAs[0]], tstream)
+                YEh.copy_(YEs[0], non_blocking=True)
+                YAh.copy_(YAs[0], non_blocking=True)
+                tstream.synchronize()
+            for _ in range(2):
+                e2e_step()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(ne):
+                e2e_step()
+            dist.barrier()
+            te = (time.perf_counter() - t0) / ne
+            tt = torch.tensor([te], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            te = float(tt.item())
+            e2e = {"value": nnz_total * nvar / te / 1e9, "unit": "Gnnz/s", "ms_per_step": 1e3 * te,
+                   "h2d_bytes_per_step": nI_d * nvar * 8 * world, "d2h_bytes_per_step": (nE_d + nA_d) * nvar * 8 * world,
+                   "api": "per rank: pinned X -> device, ib_w_apply_many_dev([EvI, AvI]), SheetMerge.run (merge across ranks), both results -> pinned host; max over ranks"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peak, peak_src = measured_peak()
-    alg = 12 * EvI.nnz + 4 * (nE_d + 1) + 8 * nvar * (nI_d + nE_d)
-    achieved = alg / (evi_ms * 1e-3) / 1e9
+    alg = 12 * nnz + 8 * nvar * (nI_d + nE_d + nA_d)
+    achieved = alg / (stack_ms * 1e-3) / 1e9
     if mergeA is not None:
         line_extra = {"merge": {"shared_E_cells": int(mergeA.parts[0]["nshared"]), "shared_A_cells": int(mergeA.parts[1]["nshared"]),
-                                "collective": "NCCL all-reduce(sum) of the shared rows' unscaled sums on a side stream, overlapping the next step's SpMMs, %d B per step" %
+                                "collective": "NCCL all-reduce(sum) of the shared rows' unscaled sums on a side stream, overlapping the next step's SpMM, %d B per step" %
                                               (mergeA.nshared * nvar * 8)}}
     else:
         line_extra = {}
+    default_wl = args.shape == "greenland_5km" and nvar == 512
     line = {"metric": "EvI/AvI apply Gnnz/s", "value": nnz_total * nvar * args.steps / (ms * 1e-3) / 1e9, "unit": "Gnnz/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, EvI.shape, AvI.shape, EvI.nnz, AvI.nnz),
-            "build_ms": {"six_matrices_median": build_med, "min": min(build_ms), "ranks": world,
+            "build_ms": {"six_matrices_median": build_med, "min": build_min, "ranks": world, "grid": args.shape,
                          "what": "regrid_matrices + matrix() x {EvI,AvI,IvE,IvA,EvA,AvE}, scale+correctA, host elevmask upload included"},
-            "roofline": {"bound": "hbm", "kernel": "spmm_tma_kernel<pair> + spmm_fixup_list_kernel (the EvI apply)", "achieved": achieved,
-                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes": alg, "ms_per_launch": evi_ms,
-                         "timing": "EvI apply alone, CUDA events around each of `steps` applies issued right after the timed region",
-                         "traffic": NCU_TRAFFIC_EVI if (args.shape == "greenland_5km" and nvar == 512) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of spmm_tma_kernel<1>, profiles/r1_spmm_tma_full_raw.csv"},
+            "roofline": {"bound": "hbm", "kernel": "spmm_stream_kernel<3> (+ spmm_stream_fixup_kernel): the stacked [EvI; AvI] apply, X read once",
+                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes": alg,
+                         "algorithmic_bytes_formula": "12*(nnz_EvI+nnz_AvI) + 8*nvar*(ncol + nrow_EvI + nrow_AvI)", "ms_per_launch": stack_ms,
+                         "timing": "one stacked apply per event pair, `steps` of them issued right after the timed region",
+                         "traffic": NCU_TRAFFIC.get("bytes") if default_wl else None, "traffic_source": NCU_TRAFFIC.get("source")},
             "gpu_launches": int(launches), "issue": ("CUDA graph of %d steps" % GSTEPS) if graph is not None else "eager",
             "clocks": sampler.result()}
     line.update(line_extra)
     if e2e is not None:
         line["e2e"] = e2e
-    if other:
-        line["other_applies"] = other
+    if more:
+        line["more"] = more
     if world == 1 and not args.no_cpu_baseline:
         _, oE, oA, bs = cpu_reference_setup(cfg)
         nf = 64

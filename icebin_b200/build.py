@@ -24,7 +24,7 @@ UNITS = {
     "couple.cu": ["-fmad=false"],
     "exgrid.cu": ["-fmad=false"],
     "hntr.cu": [],
-    "merge.cu": [],
+    "merge.cu": ["-fmad=false"],
     "capi.cu": [],
 }
 

@@ -286,7 +286,6 @@ static bool make_stream_plan(StreamPlan &P, Weighted &M1, Weighted *M2, int R, c
     IB_CUDA(cudaStreamSynchronize(s));
     const int64_t nrec = tot.y;
     if ((int)tot.z > ST_MAXN1 || (int)tot.w > ST_MAXN2 || nrec < 4096) return false;
-    if (M2 == nullptr && 10 * nrec > 7 * nnz1) return false;      // single matrix: pays only if most columns hold two nonzeros
     R = (int)std::max<int64_t>(1, std::min<int64_t>(R, nrec / (4 * ST_ROWS)));
     P.R = R;
     scan_apply<uint4>(cs, StColLoad{cnt1, cnt2}, StColOp{}, z4, StColStore{colptr.p, vbase.p}, s);
@@ -433,7 +432,12 @@ __global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = (int)(blockDim.x >> 5) - 1;     // consumer warps
     pdl_launch_dependents();
-    if (warp == 0) TRACE(0);
+    if (warp == 0) {
+        TRACE(0);
+#ifdef IB_STREAM_TRACE
+        if (lane == 0 && blockIdx.x < 8192) { unsigned sm; asm volatile("mov.u32 %0, %smid;" : "=r"(sm)); g_stream_trace[blockIdx.x * TR_N + 6] = sm; }
+#endif
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, ncw); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

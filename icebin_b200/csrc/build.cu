@@ -579,6 +579,10 @@ std::unique_ptr<Weighted> build_matrix(RegridMatrices &rm, std::string const &sp
     W->scaled = prm.scale;
     W->conservative = true;
     if (sp.combiner == 1 && prm.smooth()) {
+        // the smoothing operator lives on the ice grid (smoother.cpp:43-99 walks agridI); upstream applies it to XvA / XvE
+        // too, where rows are exchange cells and the product has no meaning: refused here instead of indexing the ice
+        // grid's tables with exchange-cell ids
+        if (sp.kindB != KI) fail(IB_ERR_ARG, "matrix %s: sigma smoothing applies to matrices whose rows are ice cells (IvA, IvE)", spec.c_str());
         W->conservative = false;              // RegridMatrices_Dynamic.cpp:167
         smooth_rows(rm, *W, prm);
     }

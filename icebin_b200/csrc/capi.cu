@@ -87,6 +87,7 @@ int64_t exgrid_rectilinear(int, const int32_t *, const double *, const int64_t *
                            double *, cudaStream_t);
 
 // merge.cu
+void multivec_to_dense(int64_t, const int64_t *, const double *, const double *, int, int64_t, double, double *, double *, cudaStream_t);
 void merge_pack(const double *, int64_t, int, const int32_t *, int64_t, double *, cudaStream_t);
 void merge_unpack(double *, int64_t, int, int64_t, const int32_t *, const double *, const double *, const double *, cudaStream_t);
 
@@ -186,6 +187,7 @@ int ib_tune(const char *key, int value)
     else if (k == "gc_nq") { if (value != 0 && value != 1 && value != 2 && value != 4) fail(IB_ERR_ARG, "ib_tune: gc_nq in {0,1,2,4}"); g_tune.gc_nq = value; }
     else if (k == "use_stream") g_tune.use_stream = value != 0;
     else if (k == "use_gc") g_tune.use_gc = value != 0;
+    else if (k == "hntr_generic") g_tune.hntr_generic = value != 0;
     else fail(IB_ERR_ARG, "ib_tune: unknown key '%s'", key);
     return IB_OK;
     IB_CATCH
@@ -785,24 +787,9 @@ int ib_multivec_to_dense(int64_t n, const int64_t *index, const double *weights,
                          double fill, double *scaleE, double *dense)
 {
     IB_TRY
-    // multivec.cpp:35-81 on host buffers (the device-resident multi-sheet merge is ib_merge_* in merge.cu)
-    for (int64_t i = 0; i < nE; ++i) scaleE[i] = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        if (index[i] < 0 || index[i] >= nE) fail(IB_ERR_ARG, "Index out of range: %ld vs. %ld", (long)index[i], (long)nE);
-        scaleE[index[i]] += weights[i];
-    }
-    for (int64_t i = 0; i < nE; ++i) scaleE[i] = 1. / scaleE[i];
-    const double nan = std::nan("");
-    for (int v = 0; v < nvar; ++v) {
-        double *d = dense + (size_t)v * nE;
-        for (int64_t i = 0; i < nE; ++i) d[i] = nan;
-        for (int64_t i = 0; i < n; ++i) {
-            int64_t e = index[i];
-            double t = vals[(size_t)i * nvar + v] * scaleE[e];
-            d[e] = std::isnan(d[e]) ? t : d[e] + t;
-        }
-        for (int64_t i = 0; i < nE; ++i) if (std::isnan(d[i])) d[i] = fill;
-    }
+    if (n < 0 || nvar < 0 || nE < 0 || (n && (!index || !weights || !vals)) || (nE && (!scaleE || (nvar && !dense))))
+        fail(IB_ERR_ARG, "ib_multivec_to_dense: bad argument");
+    multivec_to_dense(n, index, weights, vals, nvar, nE, fill, scaleE, dense, default_stream());
     return IB_OK;
     IB_CATCH
 }

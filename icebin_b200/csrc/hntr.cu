@@ -407,7 +407,7 @@ void hntr_regrid_dev(Hntr &h, const double *d_wta, double wtm, double wtb, const
     hntr_upload(h, s);
     const bool al16 = ((uintptr_t)d_src % 16 == 0) && (d_wta == nullptr || (uintptr_t)d_wta % 16 == 0);
     const int64_t ncell = (int64_t)h.imB * h.jmB;
-    if (src_dtype == IB_SRC_I16 && d_wta == nullptr && al16 && h.nested_ew && !getenv("IB_HNTR_GENERIC")) {
+    if (src_dtype == IB_SRC_I16 && d_wta == nullptr && al16 && h.nested_ew && !g_tune.hntr_generic) {
         const int nvec = h.imA / 8, cpb = h.imA / h.imB;
         const double wconst = wtm * 1.0 + wtb;
         const int64_t xb = cdiv(nvec, 128);

@@ -109,31 +109,53 @@ class SheetMerge:
             p["buf"] = self.buf_all[off: off + max(p["nshared"], 0)] if p["nshared"] else p["buf"]
             off += p["nshared"]
 
-    def begin(self, i, Y, stream):
-        p, nvar = self.parts[i], self.nvar
-        if p["nshared"]:
-            self._check(self._lib.ib_merge_pack_dev(Y.data_ptr(), nvar, nvar, p["loc"].data_ptr(), p["nshared"], p["buf"].data_ptr(), stream))
-            if self._multi:
-                p["work"] = dist.all_reduce(p["buf"], group=self.group, async_op=True)     # NCCL sum over NVLink
+    def _on(self, stream):
+        """The pack / unpack kernels and the collective must be ordered on ONE stream: torch orders NCCL against its
+        current stream, so everything runs under `with torch.cuda.stream(s)`.  `stream`: None (the current stream), a
+        torch.cuda.Stream, or a raw handle that must BE the current stream."""
+        dev = self.buf_all.device
+        if stream is None:
+            s = torch.cuda.current_stream(dev)
+        elif isinstance(stream, torch.cuda.Stream):
+            s = stream
+        else:
+            s = torch.cuda.current_stream(dev)
+            if int(stream) != s.cuda_stream:
+                raise ValueError("SheetMerge: pass a torch.cuda.Stream (or None); a raw handle must be torch's current stream, "
+                                 "otherwise the all-reduce is not ordered against the pack / unpack kernels")
+        return torch.cuda.stream(s), s.cuda_stream
 
-    def finish(self, Ys, stream):
+    def begin(self, i, Y, stream=None):
+        p, nvar = self.parts[i], self.nvar
+        ctx, h = self._on(stream)
+        with ctx:
+            if p["nshared"]:
+                self._check(self._lib.ib_merge_pack_dev(Y.data_ptr(), nvar, nvar, p["loc"].data_ptr(), p["nshared"], p["buf"].data_ptr(), h))
+                if self._multi:
+                    p["work"] = dist.all_reduce(p["buf"], group=self.group, async_op=True)     # NCCL sum over NVLink
+
+    def finish(self, Ys, stream=None):
         """Ys[i] [nrow_i, nvar] holds this sheet's unscaled sums; on return they hold the merged, scaled values."""
         nvar = self.nvar
-        for p, Y in zip(self.parts, Ys):
-            if p["work"] is not None:
-                p["work"].wait()               # current stream waits for the collective
-                p["work"] = None
-            self._check(self._lib.ib_merge_unpack_dev(Y.data_ptr(), nvar, nvar, p["nrow"], p["slot"].data_ptr(), p["buf"].data_ptr(),
-                                                      p["wtot"].data_ptr(), p["wlocal"].data_ptr(), stream))
+        ctx, h = self._on(stream)
+        with ctx:
+            for p, Y in zip(self.parts, Ys):
+                if p["work"] is not None:
+                    p["work"].wait()               # the stream waits for the collective
+                    p["work"] = None
+                self._check(self._lib.ib_merge_unpack_dev(Y.data_ptr(), nvar, nvar, p["nrow"], p["slot"].data_ptr(), p["buf"].data_ptr(),
+                                                          p["wtot"].data_ptr(), p["wlocal"].data_ptr(), h))
 
-    def run(self, Ys, stream):
+    def run(self, Ys, stream=None):
         """pack every part, ONE all-reduce of the shared rows of all parts, unpack."""
         L, nvar = self._lib, self.nvar
-        for p, Y in zip(self.parts, Ys):
-            if p["nshared"]:
-                self._check(L.ib_merge_pack_dev(Y.data_ptr(), nvar, nvar, p["loc"].data_ptr(), p["nshared"], p["buf"].data_ptr(), stream))
-        if self.nshared and self._multi:
-            dist.all_reduce(self.buf_all, group=self.group)
-        for p, Y in zip(self.parts, Ys):
-            self._check(L.ib_merge_unpack_dev(Y.data_ptr(), nvar, nvar, p["nrow"], p["slot"].data_ptr(), p["buf"].data_ptr(),
-                                              p["wtot"].data_ptr(), p["wlocal"].data_ptr(), stream))
+        ctx, h = self._on(stream)
+        with ctx:
+            for p, Y in zip(self.parts, Ys):
+                if p["nshared"]:
+                    self._check(L.ib_merge_pack_dev(Y.data_ptr(), nvar, nvar, p["loc"].data_ptr(), p["nshared"], p["buf"].data_ptr(), h))
+            if self.nshared and self._multi:
+                dist.all_reduce(self.buf_all, group=self.group)
+            for p, Y in zip(self.parts, Ys):
+                self._check(L.ib_merge_unpack_dev(Y.data_ptr(), nvar, nvar, p["nrow"], p["slot"].data_ptr(), p["buf"].data_ptr(),
+                                                  p["wtot"].data_ptr(), p["wlocal"].data_ptr(), h))

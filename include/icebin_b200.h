@@ -53,7 +53,8 @@ int ib_set_device(int device);
 int64_t ib_launch_count(void);
 /* Performance knobs; results never depend on them.  Keys: "stream_bps", "tma_bps" (CTAs per SM of the one-pass / ring
  * SpMM kernels, 1..8), "gc_nq" (64-field groups per lane of the distinct-column kernel: 0 = by nvar, 1, 2, 4),
- * "use_stream", "use_gc" (0 = route around the one-pass kernel / the distinct-column kernel). */
+ * "use_stream", "use_gc" (0 = route around the one-pass kernel / the distinct-column kernel), "hntr_generic" (1 = Hntr
+ * always takes its generic kernels). */
 int ib_tune(const char *key, int value);
 /* Return the device memory the library's stream-ordered allocations cached (cudaMemPoolTrimTo); synchronises the device. */
 int ib_trim(void);
@@ -167,12 +168,14 @@ int ib_w_apply_M(const ib_weighted *, const double *A_s, int32_t nvar, double *B
 int ib_w_apply_weight(const ib_weighted *, int dim, const double *A_s, int32_t nvar, double *out);
 
 /* coo_matvec(yy, xx, ignore_nan, nrow, ncol, row, col, data)  pylib/icebin_cython.cpp:159-192.
- * yy entries of rows with no contribution are left untouched. */
+ * yy entries of rows with no contribution are left untouched.  The ONE entry point computed on the host: a single-vector
+ * convenience of the Python binding over host arrays, not on the hot path (batched fields go through ib_w_apply*). */
 int ib_coo_matvec(double *yy, const double *xx, int ignore_nan, int64_t nrow, int64_t ncol, int64_t nnz,
                   const int32_t *row, const int32_t *col, const double *data);
 
 /* VectorMultivec::to_dense_scale + to_dense  slib/icebin/multivec.cpp:35-81: merge n sparse contributions
- * (index[n], weights[n], vals[n][nvar]) from several sheets into dense[nvar][nE]; scaleE[nE] = 1/sum(weights). */
+ * (index[n], weights[n], vals[n][nvar]) from several sheets into dense[nvar][nE]; scaleE[nE] = 1/sum(weights).
+ * Host buffers in and out, computed on the device (stable sort by cell, sums in input order: the reference's bits). */
 int ib_multivec_to_dense(int64_t n, const int64_t *index, const double *weights, const double *vals, int32_t nvar,
                          int64_t nE, double fill, double *scaleE, double *dense);
 

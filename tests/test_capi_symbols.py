@@ -80,15 +80,38 @@ def test_product_does_not_import_oracle():
 
 
 def test_host_side_helpers():
-    """coo_matvec (icebin_cython.cpp:159-192) and the VectorMultivec merge are host-array conveniences: no GPU needed."""
+    """coo_matvec (icebin_cython.cpp:159-192) is the one entry point computed on the host: a single-vector convenience of
+    the Python binding, documented as such in the header.  The VectorMultivec merge runs on the device."""
+    import torch
     from icebin_b200 import api
-    from oracle import orc
     yy = np.full(4, 7.0)
     xx = np.array([1.0, np.nan, 2.0])
     api.coo_matvec(yy, xx, True, 4, 3, [0, 0, 2, 3], [0, 1, 2, 1], [1.0, 5.0, 3.0, 4.0])
     assert list(yy) == [1.0, 7.0, 6.0, 7.0]          # rows 1 and 3 untouched, NaN input skipped
+    if not torch.cuda.is_available():
+        idx = np.array([3, 1, 3, 0]); w = np.array([2.0, 1.0, 6.0, 4.0]); v = np.array([[4.0, 1], [5.0, 2], [12.0, 3], [8.0, 4]])
+        with pytest.raises(api.IceBinError) as e:
+            api.multivec_to_dense(idx, w, v, 5, fill=-1.0)
+        assert e.value.code == -2
+
+
+@pytest.mark.gpu
+def test_multivec_to_dense_bit_exact():
+    """VectorMultivec::to_dense_scale + to_dense (multivec.cpp:35-81) on the device: entries sorted by cell (stable), summed in
+    input order with mul-then-add -- the bits of the reference's sequential loop."""
+    from icebin_b200 import api
+    from oracle import orc
     idx = np.array([3, 1, 3, 0]); w = np.array([2.0, 1.0, 6.0, 4.0]); v = np.array([[4.0, 1], [5.0, 2], [12.0, 3], [8.0, 4]])
     with np.errstate(divide="ignore"):
         s1, d1 = api.multivec_to_dense(idx, w, v, 5, fill=-1.0)
         s2, d2 = orc.multivec_to_dense(idx, w, v, 5, fill=-1.0)
     assert np.array_equal(s1, s2) and np.array_equal(d1, d2)
+    rng = np.random.default_rng(0)
+    n, nE, nvar = 200000, 5000, 3
+    idx = rng.integers(0, nE - 100, n); w = rng.uniform(0.1, 1, n); v = rng.uniform(-1, 1, (n, nvar))
+    with np.errstate(divide="ignore"):
+        s1, d1 = api.multivec_to_dense(idx, w, v, nE)
+        s2, d2 = orc.multivec_to_dense(idx, w, v, nE)
+    assert np.array_equal(s1, s2) and np.array_equal(d1, d2, equal_nan=True)
+    with pytest.raises(api.IceBinError):
+        api.multivec_to_dense(np.array([0, 7]), np.ones(2), np.ones((2, 1)), 5)

@@ -183,8 +183,10 @@ def test_row_block_sharding(cfg2, spec, nvar):
     dev = torch.device("cuda")
     X = torch.rand((M.shape[1], nvar), dtype=torch.float64, device=dev)
     Yfull = torch.empty((M.shape[0], nvar), dtype=torch.float64, device=dev)
-    if spec == "EvI":
-        M.apply_rows_dev(X.data_ptr(), nvar, nvar, Yfull.data_ptr(), nvar, 0, M.shape[0])      # same (row-chunk) plan
+    if spec in ("EvI", "AvI"):
+        # the full apply of a wide matrix takes the one-pass kernel (sums associated differently); row blocks share the
+        # row-chunk plan with the full range [0, nrow)
+        M.apply_rows_dev(X.data_ptr(), nvar, nvar, Yfull.data_ptr(), nvar, 0, M.shape[0])
     else:
         M.apply_dev(X.data_ptr(), nvar, nvar, Yfull.data_ptr(), nvar)
     Y = torch.full((M.shape[0], nvar), float("nan"), dtype=torch.float64, device=dev)

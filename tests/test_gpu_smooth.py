@@ -29,7 +29,7 @@ def test_smoothed_matrix_cfg1(cfg1, spec, sigma):
     X = np.random.default_rng(0).uniform(0, 1, (5, Wo.shape[1]))
     for fc in (False, True):
         Yo, Yg = Wo.apply(X, force_conservation=fc), Wg.apply(X, force_conservation=fc)
-        np.testing.assert_allclose(Yg, Yo, rtol=1e-11, atol=0)
+        np.testing.assert_allclose(Yg, Yo, rtol=1e-12, atol=0)
     Yg = Wg.apply(X, force_conservation=True)
     np.testing.assert_allclose((Yg * Wo.wM).sum(1), (X * Wo.Mw).sum(1), rtol=1e-12)
 
@@ -44,8 +44,16 @@ def test_smoothed_cfg2(cfg2):
     r, c, v = csc_order(*Wg.to_coo_dense())
     assert np.array_equal(r, Wo.row) and np.array_equal(c, Wo.col)
     np.testing.assert_allclose(v, Wo.val, rtol=1e-12, atol=0)
-    X = np.random.default_rng(1).uniform(0, 1, (4, Wo.shape[1]))
-    np.testing.assert_allclose(Wg.apply(X), Wo.apply(X), rtol=1e-11)
+    # the configs[2] batch: 512 fields, with and without the conservation correction, at the 1e-12 gate
+    X = np.random.default_rng(1).uniform(0, 1, (512, Wo.shape[1]))
+    for fc in (False, True):
+        np.testing.assert_allclose(Wg.apply(X, force_conservation=fc), Wo.apply(X, force_conservation=fc), rtol=1e-12, atol=0)
+    # fields of both signs: |dY| <= 1e-12 * sum |terms| of the row
+    import scipy.sparse as sp
+    Xs = np.random.default_rng(2).uniform(-1, 1, (64, Wo.shape[1]))
+    A = sp.csr_matrix((np.abs(Wo.val), (Wo.row, Wo.col)), shape=Wo.shape)
+    dY = np.abs(Wg.apply(Xs, force_conservation=False) - Wo.apply(Xs, force_conservation=False))
+    assert np.all(dY <= 1e-12 * (A @ np.abs(Xs).T).T + 1e-300)
 
 
 def test_smoothing_with_identity_dimI(cfg1):

@@ -35,6 +35,7 @@ L = lib()
 L.ib_debug_stream_trace.argtypes = [C.c_void_p, C.c_int]
 rc = L.ib_debug_stream_trace(buf.ctypes.data_as(C.c_void_p), nblk)
 assert rc == 0, rc
+np.save(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "trace_%s.npy" % which), buf)
 t = buf.astype(np.float64)
 t0 = t[:, 0].min()
 t = (t - t0) / 1e3
