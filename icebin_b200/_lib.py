@@ -73,6 +73,19 @@ SIGNATURES = {
     "ib_e1ve0c": (i64, [i32, vp, vp, i64, vp, vp, vp]),
     "ib_w_combine_chunks": (C.c_int, [i32, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
     "ib_exgrid_rectilinear": (i64, [i32, vp, vp, vp, i32, vp, i32, vp, C.c_int, vp, vp]),
+    "ib_xchg_plan": (i64, [C.c_int, vp, vp, i64, C.c_int, vp, vp, vp]),
+    "ib_xchg_create": (C.c_int, [PP, C.c_int, C.c_int, C.c_int, vp, i32]),
+    "ib_xchg_free": (None, [vp]),
+    "ib_xchg_handle_bytes": (C.c_int, []),
+    "ib_xchg_get_handle": (C.c_int, [vp, vp]),
+    "ib_xchg_open": (C.c_int, [vp, vp]),
+    "ib_xchg_open_local": (C.c_int, [vp, vp]),
+    "ib_xchg_set_part": (C.c_int, [vp, C.c_int, i64, vp, vp, vp, vp]),
+    "ib_xchg_merge_dev": (C.c_int, [vp, vp, vp, i32, vp]),
+    "ib_xchg_publish_dev": (C.c_int, [vp, vp, vp, i32, vp]),
+    "ib_xchg_gather_dev": (C.c_int, [vp, vp, vp, i32, vp]),
+    "ib_xchg_status": (C.c_int, [vp]),
+    "ib_xchg_step": (i64, [vp]),
     "ib_merge_pack_dev": (C.c_int, [vp, i64, i32, vp, i64, vp, vp]),
     "ib_merge_unpack_dev": (C.c_int, [vp, i64, i32, i64, vp, vp, vp, vp, vp]),
     "ib_hntr_create": (C.c_int, [PP, C.c_int, C.c_int, f64, f64, C.c_int, C.c_int, f64, f64, f64]),

@@ -25,6 +25,7 @@ UNITS = {
     "exgrid.cu": ["-fmad=false"],
     "hntr.cu": [],
     "merge.cu": ["-fmad=false"],
+    "xchg.cu": [],
     "capi.cu": [],
 }
 

@@ -809,6 +809,9 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
 {
     ensure_device();
     if (nvar <= 0 || W.nrow == 0) return;
+    // row_end < 0: the whole matrix through the ordinary entry points.  A caller of the row-block entry point gets the
+    // row-block kernels for every block, [0, nrow) included, so that blocks and their union agree bit for bit.
+    const bool row_api = row_end >= 0;
     if (row_end < 0) row_end = W.nrow;
     const bool ranged = !(row_begin == 0 && row_end == W.nrow);
     if (ranged) {
@@ -844,7 +847,7 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
     }
     if (ldx < nvar || ldy < nvar) fail(IB_ERR_ARG, "apply: leading dimension smaller than nvar");
     // wide matrices with about two nonzeros per column (EvI): one pass over X, no second kernel (apply_stream.cu)
-    if (!ranged && g_tune.use_stream && apply_stream(W, nullptr, dX, ldx, nvar, dY, ldy, nullptr, 0, s)) return;
+    if (!row_api && g_tune.use_stream && apply_stream(W, nullptr, dX, ldx, nvar, dY, ldy, nullptr, 0, s)) return;
     make_plan(W, s);
     ApplyPlan &P = W.plan;
     const bool vec2 = (nvar % 2 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && ((uintptr_t)dX % 16 == 0) && ((uintptr_t)dY % 16 == 0);

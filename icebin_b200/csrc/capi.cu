@@ -11,6 +11,7 @@ namespace ib {
 std::atomic<int64_t> g_launches{0};
 Tune g_tune;
 static thread_local std::string g_err;
+void set_last_error(std::string const &msg) { g_err = msg; }
 
 void ensure_device()
 {

@@ -103,6 +103,7 @@ struct DBuf {
     }
 };
 
+void set_last_error(std::string const &msg);   // what ib_last_error() returns on this thread
 void ensure_device();   // throws IB_ERR_CUDA when no CUDA device is present (no CPU fallback)
 
 }   // namespace ib

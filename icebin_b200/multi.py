@@ -159,3 +159,140 @@ class SheetMerge:
             for p, Y in zip(self.parts, Ys):
                 self._check(L.ib_merge_unpack_dev(Y.data_ptr(), nvar, nvar, p["nrow"], p["slot"].data_ptr(), p["buf"].data_ptr(),
                                                   p["wtot"].data_ptr(), p["wlocal"].data_ptr(), h))
+
+
+class PeerMerge:
+    """The merge of SheetMerge without NCCL: ranks publish the rows of their shared cells in peer-mapped memory and gather
+    their owners' rows over NVLink inside the library's own kernels (csrc/xchg.cu, ib_xchg_*): two kernel launches per
+    step, no collective call, capturable in a CUDA graph.  Results are identical on every rank (owners are added in
+    ascending rank order).
+
+    One instance per rank (process / GPU); `torch.distributed` is used ONCE, at construction, to gather the ranks' cell ids,
+    weights and IPC handles -- any host-side all-gather (MPI in the reference, GCMCoupler_ModelE.cpp:761-793) would do.
+    PeerMerge.local() builds the contexts of several ranks inside one process (tests; a host driving several GPUs)."""
+
+    def __init__(self, spaces, nvar, device, group=None):
+        """spaces: list of (n_sparse, Weighted) -- the unscaled EvI / AvI of this rank's sheet."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        mine = [(int(n), np.asarray(W.dim(0), dtype=np.int64), np.asarray(W.get_weights(0), dtype=np.float64)) for n, W in spaces]
+        if world > 1:
+            every = [None] * world
+            dist.all_gather_object(every, mine, group=group)
+        else:
+            every = [mine]
+        self._init(rank, world, every, nvar)
+        handle = self._handle()
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            self._check(self._lib.ib_xchg_open(self._h, b"".join(handles)))
+        else:
+            self._check(self._lib.ib_xchg_open(self._h, handle))
+        self._set_parts()
+
+    @classmethod
+    def local(cls, spaces_per_rank, nvar):
+        """Contexts of all ranks in this process: spaces_per_rank[r] = [(n_sparse, Weighted), ...] of rank r."""
+        import ctypes as C
+        from ._lib import vp
+        every = [[(int(n), np.asarray(W.dim(0), dtype=np.int64), np.asarray(W.get_weights(0), dtype=np.float64)) for n, W in sp]
+                 for sp in spaces_per_rank]
+        objs = []
+        for r in range(len(every)):
+            o = cls.__new__(cls)
+            o._init(r, len(every), every, nvar)
+            objs.append(o)
+        arr = (vp * len(objs))(*[o._h for o in objs])
+        for o in objs:
+            o._check(o._lib.ib_xchg_open_local(o._h, arr))
+            o._set_parts()
+        return objs
+
+    def _init(self, rank, world, every, nvar):
+        import ctypes as C
+        from ._lib import check, lib, vp
+        self._lib, self._check = lib(), check
+        self.rank, self.world, self.nvar = rank, world, nvar
+        nparts = len(every[rank])
+        self.parts = []
+        i64p = C.POINTER(C.c_int64)
+        for p in range(nparts):
+            n_sparse = every[rank][p][0]
+            ids = [np.ascontiguousarray(every[r][p][1]) for r in range(world)]
+            ptrs = (vp * world)(*[a.ctypes.data_as(vp) for a in ids])
+            cnt = (C.c_int64 * world)(*[len(a) for a in ids])
+            ns = self._lib.ib_xchg_plan(world, ptrs, cnt, n_sparse, rank, None, None, None)
+            check(ns)
+            shared = np.zeros(ns, np.int64); loc = np.zeros(ns, np.int32); owners = np.zeros(ns, np.uint64)
+            if ns:
+                check(self._lib.ib_xchg_plan(world, ptrs, cnt, n_sparse, rank, shared.ctypes.data_as(vp), loc.ctypes.data_as(vp),
+                                             owners.ctypes.data_as(vp)))
+            # summed weights of the shared cells over their owners, added in rank order
+            wtot = np.zeros(ns)
+            for r in range(world):
+                pos = {int(s): i for i, s in enumerate(ids[r])}
+                w = every[r][p][2]
+                for k, s in enumerate(shared):
+                    i = pos.get(int(s))
+                    if i is not None:
+                        wtot[k] += w[i]
+            self.parts.append(dict(n_sparse=n_sparse, nrow=len(ids[rank]), nshared=int(ns), shared_ids=shared, loc=loc, owners=owners,
+                                   wtot=wtot, wlocal=np.ascontiguousarray(every[rank][p][2])))
+        self.nshared = sum(p["nshared"] for p in self.parts)
+        h = vp()
+        ns_arr = (C.c_int64 * nparts)(*[p["nshared"] for p in self.parts])
+        check(self._lib.ib_xchg_create(C.byref(h), rank, world, nparts, ns_arr, int(nvar)))
+        self._h = h
+
+    def _handle(self):
+        import ctypes as C
+        buf = C.create_string_buffer(self._lib.ib_xchg_handle_bytes())
+        self._check(self._lib.ib_xchg_get_handle(self._h, buf))
+        return buf.raw
+
+    def _set_parts(self):
+        from ._lib import vp
+        for i, p in enumerate(self.parts):
+            self._check(self._lib.ib_xchg_set_part(self._h, i, p["nrow"], p["loc"].ctypes.data_as(vp), p["owners"].ctypes.data_as(vp),
+                                                   p["wtot"].ctypes.data_as(vp), p["wlocal"].ctypes.data_as(vp)))
+
+    def _args(self, Ys):
+        import ctypes as C
+        from ._lib import vp
+        n = len(self.parts)
+        return (vp * n)(*[y.data_ptr() for y in Ys]), (C.c_int64 * n)(*[y.stride(0) for y in Ys])
+
+    def args(self, Ys):
+        """Pre-built C argument arrays for merge_raw (the per-step Python cost matters at a 60 us step)."""
+        return self._args(Ys)
+
+    def merge(self, Ys, stream=0):
+        """Ys[p]: [nrow_p, nvar] unscaled sums in, merged and scaled values out (device tensors, in place)."""
+        yp, ld = self._args(Ys)
+        self._check(self._lib.ib_xchg_merge_dev(self._h, yp, ld, Ys[0].shape[1], stream or None))
+
+    def merge_raw(self, yp, ld, nvar, stream):
+        self._check(self._lib.ib_xchg_merge_dev(self._h, yp, ld, nvar, stream))
+
+    def publish(self, Ys, stream=0):
+        yp, ld = self._args(Ys)
+        self._check(self._lib.ib_xchg_publish_dev(self._h, yp, ld, Ys[0].shape[1], stream or None))
+
+    def gather(self, Ys, stream=0):
+        yp, ld = self._args(Ys)
+        self._check(self._lib.ib_xchg_gather_dev(self._h, yp, ld, Ys[0].shape[1], stream or None))
+
+    def status(self):
+        self._check(self._lib.ib_xchg_status(self._h))
+
+    def steps_done(self):
+        return int(self._lib.ib_xchg_step(self._h))
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.ib_xchg_free(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -187,6 +187,38 @@ int ib_merge_pack_dev(const double *dY, int64_t ldy, int32_t nvar, const int32_t
 int ib_merge_unpack_dev(double *dY, int64_t ldy, int32_t nvar, int64_t nrow, const int32_t *d_slot_of_row,
                         const double *d_buf, const double *d_wtot, const double *d_wlocal, void *stream);
 
+/* ---- The same merge across GPUs over NVLink peer memory (one rank = one process = one GPU = one ice sheet) ----------
+ * Replaces the MPI gather to the GCM root + VectorMultivec merge (modele/GCMCoupler_ModelE.cpp:761-793, multivec.cpp:35-81)
+ * for results that stay in HBM: a rank publishes the rows of its shared cells in a buffer its peers have mapped (CUDA IPC)
+ * and gathers, for every shared cell it holds, the owners' rows with plain loads over NVLink, added in ascending rank order
+ * (the same bits on every rank), times 1 / (summed weights); rows of cells no other sheet touches are divided by their own
+ * weight.  Two kernels per step, no host round trip, capturable in a CUDA graph; a step counter in device memory and
+ * ready / done flags in the publisher's memory order the ranks (waits give up after 4 s: ib_xchg_status).
+ *
+ *   host (all ranks):  gather every rank's dims[0] ids  ->  ib_xchg_plan  ->  ib_xchg_create  ->  all-gather the handles
+ *                      ->  ib_xchg_open  ->  ib_xchg_set_part (per grid: E, A)  ->  ib_xchg_merge_dev every step.
+ * Up to 64 ranks, up to 4 parts (grids) per context.  Ranks of ONE process use ib_xchg_open_local instead of IPC handles.
+ * Kernels of different ranks wait on each other, so they must run on different GPUs; on one GPU drive the ranks one after
+ * the other with ib_xchg_publish_dev (all ranks) and then ib_xchg_gather_dev (all ranks). */
+typedef struct ib_xchg ib_xchg;
+/* shared cells of two or more ranks, ascending: ids[r][n[r]] = rank r's dims[0]; shared == NULL returns the count */
+int64_t ib_xchg_plan(int nranks, const int64_t *const *ids, const int64_t *n, int64_t n_sparse, int rank, int64_t *shared,
+                     int32_t *loc, uint64_t *owners);
+int ib_xchg_create(ib_xchg **out, int rank, int nranks, int nparts, const int64_t *nshared, int32_t nvar_max);
+void ib_xchg_free(ib_xchg *);
+int ib_xchg_handle_bytes(void);                                  /* sizeof(cudaIpcMemHandle_t) */
+int ib_xchg_get_handle(const ib_xchg *, void *handle);
+int ib_xchg_open(ib_xchg *, const void *handles);                /* [nranks][ib_xchg_handle_bytes()], all-gathered by the host */
+int ib_xchg_open_local(ib_xchg *, ib_xchg *const *peers);        /* peers[r] = rank r's context in this process */
+int ib_xchg_set_part(ib_xchg *, int part, int64_t nrow, const int32_t *loc, const uint64_t *owners, const double *wtot,
+                     const double *wlocal);
+/* dY[p]: [nrow_p][ldy_p] unscaled sums of part p in, merged and scaled values out */
+int ib_xchg_merge_dev(ib_xchg *, double *const *dY, const int64_t *ldy, int32_t nvar, void *stream);
+int ib_xchg_publish_dev(ib_xchg *, double *const *dY, const int64_t *ldy, int32_t nvar, void *stream);
+int ib_xchg_gather_dev(ib_xchg *, double *const *dY, const int64_t *ldy, int32_t nvar, void *stream);
+int ib_xchg_status(ib_xchg *);                                   /* IB_ERR_CUDA if a wait on a peer timed out; synchronises */
+int64_t ib_xchg_step(ib_xchg *);                                 /* steps completed so far; synchronises */
+
 /* ---- Coupling step, regridding side (callers of the path: SURVEY 8f rank 2) ---------------------------- */
 /* Variable/unit transformation in front of a regrid apply:  Z = O * M + b.replicate(ncell, 1)
  *   gcm -> ice: ice_ivalsI = IvE0 * (gcm_ovalsE0 * ivg.M + ivg.b)        IceCoupler.cpp:203-252
