@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="kernel experiments only; the driver never passes this")
     ap.add_argument("--no-more", action="store_true", help="skip the secondary measurements (`more`)")
+    ap.add_argument("--merge", default="peer", choices=["peer", "nccl"],
+                    help="N>1: merge of the sheets' A/E contributions by the library's peer-memory kernels (default) or an NCCL all-reduce")
     return ap.parse_args()
 
 
@@ -424,19 +426,27 @@ def run_b200(args):
     YE = torch.empty((nE_d, nvar), dtype=torch.float64, device=dev)
     YA = torch.empty((nA_d, nvar), dtype=torch.float64, device=dev)
 
-    # multi-sheet merge (N>1): as in the coupler (IceCoupler.cpp:371-377, 445-457) the sheets apply UNSCALED EvI/AvI and
-    # the GCM side divides the summed contributions by the summed weights (multivec.cpp:35-81)
+    # multi-sheet merge (N>1): the GCM side sums the sheets' contributions and divides by the summed weights (multivec.cpp:35-81)
     mergeA = None
     if world > 1:
         from icebin_b200 import multi
-        rm_u = gcm.regrid_matrices(sh.name, em_host, scale=False, correctA=True)
-        EvI, AvI = rm_u.matrix("EvI"), rm_u.matrix("AvI")
-        assert (EvI.shape, AvI.shape) == ((nE_d, nI_d), (nA_d, nI_d))
-        # two merge contexts + two sets of result buffers: the exchange of step s runs on a side stream while the
-        # SpMMs of step s+1 run on the main one (batches of fields are independent)
-        merges = [multi.SheetMerge([(gcm.nE, EvI), (gcm.nA, AvI)], nvar, dev) for _ in range(2)]
-        mergeA = merges[0]
-        side = torch.cuda.Stream(device=dev)
+        # two sets of result buffers: the exchange of step s runs on a side stream while the SpMM of step s+1 runs on the
+        # main one (batches of fields are independent)
+        if args.merge == "peer":
+            # the library's own publish / gather kernels over NVLink peer memory (csrc/xchg.cu), no collective call.  The
+            # sheets apply their SCALED matrices, so the rows of unshared cells are final and only the shared cells travel
+            # (as sum = Y * wM) and are rewritten: sum over owners / summed weights (multivec.cpp:35-81)
+            peer = multi.PeerMerge([(gcm.nE, EvI), (gcm.nA, AvI)], nvar, dev, scaled=True)
+            mergeA = peer
+            api.tune("stream_spare", 8)      # the small merge kernels need a free CTA slot next to the SpMM's resident grid
+        else:
+            # as in the coupler (IceCoupler.cpp:371-377, 445-457): UNSCALED EvI / AvI, pack + NCCL all-reduce + unpack
+            rm_u = gcm.regrid_matrices(sh.name, em_host, scale=False, correctA=True)
+            EvI, AvI = rm_u.matrix("EvI"), rm_u.matrix("AvI")
+            assert (EvI.shape, AvI.shape) == ((nE_d, nI_d), (nA_d, nI_d))
+            merges = [multi.SheetMerge([(gcm.nE, EvI), (gcm.nA, AvI)], nvar, dev) for _ in range(2)]
+            mergeA = merges[0]
+        side = torch.cuda.Stream(device=dev, priority=-1)       # the small merge kernels go first when a CTA slot frees up
         YEs = [YE, torch.empty_like(YE)]
         YAs = [YA, torch.empty_like(YA)]
         spmm_done = [torch.cuda.Event() for _ in range(2)]
@@ -453,6 +463,9 @@ def run_b200(args):
         _Yp = [(_vp * 2)(YEs[k].data_ptr(), YAs[k].data_ptr()) for k in range(2)]
     _apply_many = lib().ib_w_apply_many_dev
     _X, _st = _vp(X.data_ptr()), _vp(stream)
+    if mergeA is not None and args.merge == "peer":
+        _pa = [peer.args([YEs[k], YAs[k]]) for k in range(2)]
+        _side = _vp(side.cuda_stream)
     step_no = [0]
     fresh = [True, True]       # no exchange pending on buffer set k (start of the run / of a captured graph)
 
@@ -470,7 +483,10 @@ def run_b200(args):
         check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[k], _ld2, 1, _st))
         spmm_done[k].record(tstream)
         side.wait_event(spmm_done[k])
-        merges[k].run([YEs[k], YAs[k]], side)
+        if args.merge == "peer":
+            peer.merge_raw(_pa[k][0], _pa[k][1], nvar, _side)
+        else:
+            merges[k].run([YEs[k], YAs[k]], side)
         merge_done[k].record(side)
 
     def drain():
@@ -492,9 +508,10 @@ def run_b200(args):
     # launches included) and its stream-ordered allocations are capturable.
     GSTEPS = 8
     graph, launches_per_graph = None, None
-    # single-GPU only: with NCCL inside the capture one rank falling back to eager while another replays would
-    # desynchronise the collectives
-    if not args.no_graph and args.steps >= GSTEPS and world == 1:
+    # N>1 with the peer merge: nothing but the library's kernels is captured (no collective call), every rank captures the
+    # same GSTEPS steps.  With NCCL inside the capture one rank falling back to eager while another replays would
+    # desynchronise the collectives, so that arm stays eager.
+    if not args.no_graph and args.steps >= GSTEPS and (world == 1 or args.merge == "peer"):
         try:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
@@ -608,7 +625,10 @@ def run_b200(args):
             def e2e_step():
                 X.copy_(Xh, non_blocking=True)
                 check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[0], _ld2, 1, _st))
-                merges[0].run([YEs[0], YAs[0]], tstream)
+                if args.merge == "peer":
+                    peer.merge_raw(_pa[0][0], _pa[0][1], nvar, _st)
+                else:
+                    merges[0].run([YEs[0], YAs[0]], tstream)
                 YEh.copy_(YEs[0], non_blocking=True)
                 YAh.copy_(YAs[0], non_blocking=True)
                 tstream.synchronize()
@@ -625,8 +645,12 @@ def run_b200(args):
             te = float(tt.item())
             e2e = {"value": nnz_total * nvar / te / 1e9, "unit": "Gnnz/s", "ms_per_step": 1e3 * te,
                    "h2d_bytes_per_step": nI_d * nvar * 8 * world, "d2h_bytes_per_step": (nE_d + nA_d) * nvar * 8 * world,
-                   "api": "per rank: pinned X -> device, ib_w_apply_many_dev([EvI, AvI]), SheetMerge.run (merge across ranks), both results -> pinned host; max over ranks"}
+                   "api": "per rank: pinned X -> device, ib_w_apply_many_dev([EvI, AvI]), merge across ranks (%s), both results -> pinned host; max over ranks" %
+                          ("ib_xchg_merge_dev" if args.merge == "peer" else "SheetMerge.run: NCCL")}
 
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()          # nobody unmaps its exchange buffer while a peer may still read it
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -634,9 +658,12 @@ def run_b200(args):
     alg = 12 * nnz + 8 * nvar * (nI_d + nE_d + nA_d)
     achieved = alg / (stack_ms * 1e-3) / 1e9
     if mergeA is not None:
+        how = ("ib_xchg_merge_dev: every rank publishes the rows of its shared cells in peer-mapped memory and gathers its owners' rows over NVLink "
+               "(two kernels, no collective call), on a side stream, overlapping the next step's SpMM; at most %d B published per rank and step"
+               if args.merge == "peer" else
+               "NCCL all-reduce(sum) of the shared rows' unscaled sums on a side stream, overlapping the next step's SpMM, %d B per step")
         line_extra = {"merge": {"shared_E_cells": int(mergeA.parts[0]["nshared"]), "shared_A_cells": int(mergeA.parts[1]["nshared"]),
-                                "collective": "NCCL all-reduce(sum) of the shared rows' unscaled sums on a side stream, overlapping the next step's SpMM, %d B per step" %
-                                              (mergeA.nshared * nvar * 8)}}
+                                "how": how % (mergeA.nshared * nvar * 8)}}
     else:
         line_extra = {}
     default_wl = args.shape == "greenland_5km" and nvar == 512

@@ -80,7 +80,7 @@ SIGNATURES = {
     "ib_xchg_get_handle": (C.c_int, [vp, vp]),
     "ib_xchg_open": (C.c_int, [vp, vp]),
     "ib_xchg_open_local": (C.c_int, [vp, vp]),
-    "ib_xchg_set_part": (C.c_int, [vp, C.c_int, i64, vp, vp, vp, vp]),
+    "ib_xchg_set_part": (C.c_int, [vp, C.c_int, i64, vp, vp, vp, vp, C.c_int]),
     "ib_xchg_merge_dev": (C.c_int, [vp, vp, vp, i32, vp]),
     "ib_xchg_publish_dev": (C.c_int, [vp, vp, vp, i32, vp]),
     "ib_xchg_gather_dev": (C.c_int, [vp, vp, vp, i32, vp]),

@@ -583,7 +583,7 @@ bool apply_stream(Weighted &M1, Weighted *M2, const double *dX, int64_t ldx, int
     if (M2) IB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_stream_kernel<3>, 32 * (ncw + 1), smem));
     else IB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmm_stream_kernel<2>, 32 * (ncw + 1), smem));
     if (occ < 1) return false;
-    const int R = std::max(1, sm_count() * std::min(bps, occ) / ntile);
+    const int R = std::max(1, (sm_count() * std::min(bps, occ) - g_tune.stream_spare) / ntile);
     StreamPlan &P = M1.stream_plan;
     if (!make_stream_plan(P, M1, M2, R, s)) return false;
     const int64_t ldp = (int64_t)ntile * tw;

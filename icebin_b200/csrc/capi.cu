@@ -32,10 +32,16 @@ int device_index()
     return dev;
 }
 
-// Freed blocks stay in the device's default memory pool up to this many bytes (steady-state matrix builds then never
-// reach the driver allocator); what exceeds it goes back to the driver at the next synchronisation, so a co-resident
-// allocator (the host application's) is not starved.  ib_trim() releases everything.
-constexpr uint64_t POOL_KEEP_BYTES = 2ull << 30;
+// Freed blocks stay in the device's default memory pool up to 1/8 of the device's memory (steady-state matrix builds --
+// ~10 GB of temporaries for a 36 M-cell sheet -- then never reach the driver allocator); what exceeds it goes back to the
+// driver at the next synchronisation, so a co-resident allocator (the host application's) is not starved.  ib_trim()
+// releases everything.
+static uint64_t pool_keep_bytes()
+{
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return 4ull << 30; }
+    return std::max<uint64_t>(4ull << 30, tot / 8);
+}
 
 cudaStream_t default_stream()
 {
@@ -49,8 +55,9 @@ cudaStream_t default_stream()
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             uint64_t thr = 0;
             cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            if (thr < POOL_KEEP_BYTES) {          // never lower a threshold the host application has raised
-                thr = POOL_KEEP_BYTES;
+            const uint64_t keep = pool_keep_bytes();
+            if (thr < keep) {                     // never lower a threshold the host application has raised
+                thr = keep;
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
             }
         }
@@ -184,6 +191,7 @@ int ib_tune(const char *key, int value)
     if (!key) fail(IB_ERR_ARG, "ib_tune: null key");
     const std::string k(key);
     if (k == "stream_bps") { if (value < 1 || value > 8) fail(IB_ERR_ARG, "ib_tune: stream_bps in 1..8"); g_tune.stream_bps = value; }
+    else if (k == "stream_spare") { if (value < 0 || value > 64) fail(IB_ERR_ARG, "ib_tune: stream_spare in 0..64"); g_tune.stream_spare = value; }
     else if (k == "tma_bps") { if (value < 1 || value > 8) fail(IB_ERR_ARG, "ib_tune: tma_bps in 1..8"); g_tune.tma_bps = value; }
     else if (k == "gc_nq") { if (value != 0 && value != 1 && value != 2 && value != 4) fail(IB_ERR_ARG, "ib_tune: gc_nq in {0,1,2,4}"); g_tune.gc_nq = value; }
     else if (k == "use_stream") g_tune.use_stream = value != 0;

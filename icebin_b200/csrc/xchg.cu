@@ -39,6 +39,7 @@ static_assert(sizeof(XHdr) == 128, "header is one 128-byte line");
 
 struct XPart {
     int64_t nrow = 0, nshared = 0, off = 0;      // off: first row of the part in the exchange buffer
+    int scaled = 0;           // rows of Y arrive already divided by wlocal (a scaled matrix): only shared rows are touched
     DBuf<int32_t> loc;        // [nshared] local dense row or -1
     DBuf<int32_t> slot;       // [nrow] shared slot of a local row or -1
     DBuf<uint64_t> owners;    // [nshared] bit r: rank r holds the cell
@@ -103,6 +104,7 @@ __device__ void xchg_wait(const unsigned long long *peers, uint64_t mask, int fi
 
 struct XPartDev {
     int64_t nrow, nshared, off;
+    int scaled;
     const int32_t *loc, *slot;
     const uint64_t *owners;
     const double *wtot, *wlocal;
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(256) xchg_publish_kernel(const XArgs a)
         if (r < 0) continue;                     // not mine: nobody reads this row of my buffer
         const double *y = P.Y + (int64_t)r * P.ldy + f;
         double2 v = make_double2(y[0], f + 1 < a.nvar ? y[1] : 0.0);
+        if (P.scaled) { const double w = P.wlocal[r]; v.x *= w; v.y *= w; }      // back to this sheet's unscaled sum
         *reinterpret_cast<double2 *>(buf + g * a.ldb + f) = v;
     }
     __threadfence_system();
@@ -158,18 +161,29 @@ __global__ void __launch_bounds__(256) xchg_gather_kernel(const XArgs a)
     const unsigned long long s = *a.step;
     xchg_wait(a.peers, a.reads_mask, 0, s + 1, a.err);
     const int nv2 = (a.nvar + 1) / 2;
-    int64_t rows = 0;
-    for (int p = 0; p < a.nparts; ++p) rows += a.part[p].nrow;
-    const int64_t work = rows * nv2;
+    // work items: every local row of an unscaled part, only the shared cells of a scaled part
+    int64_t cum[XCHG_MAX_PARTS + 1];
+    cum[0] = 0;
+    for (int p = 0; p < a.nparts; ++p) cum[p + 1] = cum[p] + (a.part[p].scaled ? a.part[p].nshared : a.part[p].nrow);
+    const int64_t work = cum[a.nparts] * nv2;
     const int64_t boff = sizeof(XHdr) / sizeof(double) + (int64_t)(s & 1) * a.total * a.ldb;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t g = t / nv2;
         const int f = (int)(t - g * nv2) * 2;
         int p = 0;
-        while (p + 1 < a.nparts && g >= a.part[p].nrow) { g -= a.part[p].nrow; ++p; }
+        while (p + 1 < a.nparts && g >= cum[p + 1]) ++p;
+        g -= cum[p];
         const XPartDev &P = a.part[p];
+        int32_t k;
+        if (P.scaled) {
+            k = (int32_t)g;
+            const int32_t r = P.loc[k];
+            if (r < 0) continue;                            // not one of my cells
+            g = r;
+        } else {
+            k = P.slot[g];
+        }
         double *y = P.Y + g * P.ldy + f;
-        const int32_t k = P.slot[g];
         double2 v;
         double sc;
         if (k >= 0) {
@@ -209,7 +223,7 @@ static XArgs make_args(Xchg &x, double *const *dY, const int64_t *ldy, int nvar)
         if (P.nrow > 0 && !P.slot.p) fail(IB_ERR_ARG, "ib_xchg: part %d has no plan (ib_xchg_set_part)", p);
         if (!dY[p] && P.nrow > 0) fail(IB_ERR_ARG, "ib_xchg: null result buffer");
         if (ldy[p] < nvar) fail(IB_ERR_ARG, "ib_xchg: leading dimension smaller than nvar");
-        a.part[p] = XPartDev{P.nrow, P.nshared, P.off, P.loc.p, P.slot.p, P.owners.p, P.wtot.p, P.wlocal.p, dY[p], ldy[p]};
+        a.part[p] = XPartDev{P.nrow, P.nshared, P.off, P.scaled, P.loc.p, P.slot.p, P.owners.p, P.wtot.p, P.wlocal.p, dY[p], ldy[p]};
     }
     a.peers = x.d_peer.p;
     a.reads_mask = x.reads_mask; a.readers_mask = x.readers_mask;
@@ -229,7 +243,7 @@ void xchg_gather(Xchg &x, double *const *dY, const int64_t *ldy, int nvar, cudaS
 {
     XArgs a = make_args(x, dY, ldy, nvar);
     int64_t rows = 0;
-    for (auto &P : x.parts) rows += P.nrow;
+    for (auto &P : x.parts) rows += P.scaled ? P.nshared : P.nrow;
     const int64_t work = std::max<int64_t>(1, rows * ((nvar + 1) / 2));
     const unsigned grid = (unsigned)std::min<int64_t>(cdiv(work, 256), 2 * sm_count());
     xchg_gather_kernel<<<grid, 256, 0, s>>>(a);
@@ -361,8 +375,12 @@ int ib_xchg_open_local(ib_xchg *h, ib_xchg *const *peers)
 
 /* Plan of part `part` (all host arrays): nrow local dense rows; for the part's shared cells k (the same list, in the same
  * order, on every rank): loc[k] = local row or -1, owners[k] = bit mask of the ranks holding the cell, wtot[k] = summed
- * weights over the owners; wlocal[nrow] = this rank's weights (wM of the unscaled matrix). */
-int ib_xchg_set_part(ib_xchg *h, int part, int64_t nrow, const int32_t *loc, const uint64_t *owners, const double *wtot, const double *wlocal)
+ * weights over the owners; wlocal[nrow] = this rank's weights (wM of the matrix).  scaled = 0: Y holds the UNSCALED sums
+ * (the coupler's E1vI_unscaled, IceCoupler.cpp:371-377) and every row is divided by its weight here; scaled = 1: Y comes from
+ * the SCALED matrix (rows already divided by wlocal), so only the shared cells are touched: a rank publishes Y * wlocal
+ * and the rows of unshared cells are final as they are. */
+int ib_xchg_set_part(ib_xchg *h, int part, int64_t nrow, const int32_t *loc, const uint64_t *owners, const double *wtot, const double *wlocal,
+                     int scaled)
 {
     X_TRY
     if (!h || part < 0 || part >= (int)h->x.parts.size() || nrow < 0) fail(IB_ERR_ARG, "ib_xchg_set_part: bad argument");
@@ -371,6 +389,7 @@ int ib_xchg_set_part(ib_xchg *h, int part, int64_t nrow, const int32_t *loc, con
     if ((P.nshared && (!loc || !owners || !wtot)) || (nrow && !wlocal)) fail(IB_ERR_ARG, "ib_xchg_set_part: null array");
     cudaStream_t s = x.stream;
     P.nrow = nrow;
+    P.scaled = scaled != 0;
     std::vector<int32_t> slot((size_t)nrow, -1);
     for (int64_t k = 0; k < P.nshared; ++k) {
         const bool mine = loc[k] >= 0;

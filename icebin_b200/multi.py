@@ -171,8 +171,10 @@ class PeerMerge:
     weights and IPC handles -- any host-side all-gather (MPI in the reference, GCMCoupler_ModelE.cpp:761-793) would do.
     PeerMerge.local() builds the contexts of several ranks inside one process (tests; a host driving several GPUs)."""
 
-    def __init__(self, spaces, nvar, device, group=None):
-        """spaces: list of (n_sparse, Weighted) -- the unscaled EvI / AvI of this rank's sheet."""
+    def __init__(self, spaces, nvar, device, group=None, scaled=False):
+        """spaces: list of (n_sparse, Weighted) -- the EvI / AvI of this rank's sheet: unscaled (the coupler's matrices; every
+        row is divided by its weight in the merge) or, with scaled=True, scaled (only the shared cells are touched)."""
+        self.scaled = bool(scaled)
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         mine = [(int(n), np.asarray(W.dim(0), dtype=np.int64), np.asarray(W.get_weights(0), dtype=np.float64)) for n, W in spaces]
@@ -192,7 +194,7 @@ class PeerMerge:
         self._set_parts()
 
     @classmethod
-    def local(cls, spaces_per_rank, nvar):
+    def local(cls, spaces_per_rank, nvar, scaled=False):
         """Contexts of all ranks in this process: spaces_per_rank[r] = [(n_sparse, Weighted), ...] of rank r."""
         import ctypes as C
         from ._lib import vp
@@ -201,6 +203,7 @@ class PeerMerge:
         objs = []
         for r in range(len(every)):
             o = cls.__new__(cls)
+            o.scaled = bool(scaled)
             o._init(r, len(every), every, nvar)
             objs.append(o)
         arr = (vp * len(objs))(*[o._h for o in objs])
@@ -255,7 +258,7 @@ class PeerMerge:
         from ._lib import vp
         for i, p in enumerate(self.parts):
             self._check(self._lib.ib_xchg_set_part(self._h, i, p["nrow"], p["loc"].ctypes.data_as(vp), p["owners"].ctypes.data_as(vp),
-                                                   p["wtot"].ctypes.data_as(vp), p["wlocal"].ctypes.data_as(vp)))
+                                                   p["wtot"].ctypes.data_as(vp), p["wlocal"].ctypes.data_as(vp), int(self.scaled)))
 
     def _args(self, Ys):
         import ctypes as C

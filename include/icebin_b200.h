@@ -52,7 +52,7 @@ int ib_set_device(int device);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 int64_t ib_launch_count(void);
 /* Performance knobs; results never depend on them.  Keys: "stream_bps", "tma_bps" (CTAs per SM of the one-pass / ring
- * SpMM kernels, 1..8), "gc_nq" (64-field groups per lane of the distinct-column kernel: 0 = by nvar, 1, 2, 4),
+ * SpMM kernels, 1..8), "stream_spare" (CTA slots the one-pass kernel leaves free for a concurrent small kernel, 0..64), "gc_nq" (64-field groups per lane of the distinct-column kernel: 0 = by nvar, 1, 2, 4),
  * "use_stream", "use_gc" (0 = route around the one-pass kernel / the distinct-column kernel), "hntr_generic" (1 = Hntr
  * always takes its generic kernels). */
 int ib_tune(const char *key, int value);
@@ -210,8 +210,10 @@ int ib_xchg_handle_bytes(void);                                  /* sizeof(cudaI
 int ib_xchg_get_handle(const ib_xchg *, void *handle);
 int ib_xchg_open(ib_xchg *, const void *handles);                /* [nranks][ib_xchg_handle_bytes()], all-gathered by the host */
 int ib_xchg_open_local(ib_xchg *, ib_xchg *const *peers);        /* peers[r] = rank r's context in this process */
+/* scaled = 0: dY holds unscaled sums (the coupler's E1vI_unscaled) and every row is divided by its weight in the merge;
+ * scaled = 1: dY comes from the scaled matrix, only the shared cells are touched (Y * wlocal is what travels) */
 int ib_xchg_set_part(ib_xchg *, int part, int64_t nrow, const int32_t *loc, const uint64_t *owners, const double *wtot,
-                     const double *wlocal);
+                     const double *wlocal, int scaled);
 /* dY[p]: [nrow_p][ldy_p] unscaled sums of part p in, merged and scaled values out */
 int ib_xchg_merge_dev(ib_xchg *, double *const *dY, const int64_t *ldy, int32_t nvar, void *stream);
 int ib_xchg_publish_dev(ib_xchg *, double *const *dY, const int64_t *ldy, int32_t nvar, void *stream);

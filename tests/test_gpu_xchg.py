@@ -29,11 +29,13 @@ def three_sheets():
     return gcm, mats
 
 
-@pytest.mark.parametrize("nvar", [6, 65])
-def test_three_ranks_in_one_process(nvar):
+@pytest.mark.parametrize("nvar,scaled", [(6, False), (65, False), (64, True)])
+def test_three_ranks_in_one_process(nvar, scaled):
+    """scaled=False: the coupler's unscaled matrices, every row divided by its weight in the merge; scaled=True: scaled
+    matrices, only the shared cells travel (as Y * wM) and are rewritten."""
     gcm, mats = three_sheets()
     dev = torch.device("cuda")
-    ctx = multi.PeerMerge.local([[(gcm.nE, E), (gcm.nA, A)] for E, A in mats], nvar)
+    ctx = multi.PeerMerge.local([[(gcm.nE, E), (gcm.nA, A)] for E, A in mats], nvar, scaled=scaled)
     assert ctx[0].nshared > 0 and any((p["owners"] == 7).any() for p in ctx[0].parts), "some cell should have three owners"
     rng = np.random.default_rng(0)
     for step in range(5):                       # > 2 steps: both buffers are reused
@@ -45,7 +47,11 @@ def test_three_ranks_in_one_process(nvar):
             E.apply_dev(X.data_ptr(), nvar, nvar, ye.data_ptr(), nvar)
             A.apply_dev(X.data_ptr(), nvar, nvar, ya.data_ptr(), nvar)
             torch.cuda.synchronize()
-            Ys.append([ye, ya]); num.append([ye.cpu().numpy().copy(), ya.cpu().numpy().copy()])
+            num.append([ye.cpu().numpy().copy(), ya.cpu().numpy().copy()])
+            if scaled:          # what the scaled matrices would have produced
+                ye /= torch.from_numpy(E.get_weights(0)).to(dev)[:, None]
+                ya /= torch.from_numpy(A.get_weights(0)).to(dev)[:, None]
+            Ys.append([ye, ya])
         for r in range(3):
             ctx[r].publish(Ys[r])
         torch.cuda.synchronize()
@@ -55,7 +61,7 @@ def test_three_ranks_in_one_process(nvar):
         for p, n_sparse in ((0, gcm.nE), (1, gcm.nA)):
             ref = multi.merge_reference([(mats[r][p].dim(0), mats[r][p].get_weights(0), num[r][p]) for r in range(3)], n_sparse)
             for r in range(3):
-                np.testing.assert_allclose(Ys[r][p].cpu().numpy(), ref[mats[r][p].dim(0)], rtol=1e-13, atol=0)
+                np.testing.assert_allclose(Ys[r][p].cpu().numpy(), ref[mats[r][p].dim(0)], rtol=1e-13 if not scaled else 1e-12, atol=0)
         # every owner of a shared cell holds the same bits
         for p in range(2):
             a, b = mats[0][p].dim(0), mats[1][p].dim(0)

@@ -76,6 +76,23 @@ def timed(fn, n=200):
     return float(t.item()) * 1e3
 
 
+# scaled mode: the sheets' SCALED matrices, only the shared cells travel
+rms = gcm.regrid_matrices(sh.name, em, scale=True, correctA=True)
+EvIs, AvIs = rms.matrix("EvI"), rms.matrix("AvI")
+peer_s = multi.PeerMerge([(gcm.nE, EvIs), (gcm.nA, AvIs)], nvar, dev, scaled=True)
+api.tune("stream_spare", 8)
+
+
+def spmm_s():
+    api.apply_many_dev([EvIs, AvIs], X.data_ptr(), nvar, nvar, [YE.data_ptr(), YA.data_ptr()], [nvar, nvar], True, S)
+
+
+for rep in range(3):
+    spmm_s(); peer_s.merge([YE, YA], S); torch.cuda.synchronize()
+    assert torch.allclose(YE, refE, rtol=1e-12, atol=0) and torch.allclose(YA, refA, rtol=1e-12, atol=0), "scaled peer merge differs"
+peer_s.status()
+yps, lds = peer_s.args([YE, YA])
+out["us_spmm_plus_scaled_peer_merge_eager"] = timed(lambda: (spmm_s(), peer_s.merge_raw(yps, lds, nvar, S)))
 yp, ld = peer.args([YE, YA])
 out["us_spmm_only"] = timed(spmm)
 out["us_spmm_plus_nccl_merge_eager"] = timed(lambda: (spmm(), nccl.run([YE, YA], st)))
