@@ -201,11 +201,13 @@ def ev_time(torch, fn, n, warm=3):
 
 
 def timed_build(torch, gcm, name, em, specs, reps, **kw):
+    """em: host array (uploaded inside the timed region, as a host caller's would be) or a device tensor (resident)."""
     ts = []
+    on_dev = hasattr(em, "data_ptr")
     for it in range(reps + 2):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        rm = gcm.regrid_matrices(name, em, **kw)
+        rm = gcm.regrid_matrices_dev(name, em.data_ptr(), **kw) if on_dev else gcm.regrid_matrices(name, em, **kw)
         mats = {s: rm.matrix(s) for s in specs}
         torch.cuda.synchronize()
         if it >= 2:
@@ -307,8 +309,11 @@ def more_single_gpu(torch, api, args, cfg, gcm, mats, X, YE, YA, stream, peak, n
         g1 = api.GCMRegridder(gA, cfg["hcdefs"], True)
         g1.add_sheet(gr.name, gr)
         med, mn = timed_build(torch, g1, gr.name, em1, SIX, 5, scale=True, correctA=True)
+        em1d = torch.from_numpy(em1).to(dev)
+        medd, mnd = timed_build(torch, g1, gr.name, em1d, SIX, 5, scale=True, correctA=True)
         return {"six_matrices_median_ms": med, "min_ms": mn, "nI": gr.nI, "nX": gr.nX, "target_ms": 100.0,
-                "what": "regrid_matrices + matrix() x {EvI,AvI,IvE,IvA,EvA,AvE}, scale+correctA, wall clock, host elevmask upload (34 MB) included"}
+                "what": "regrid_matrices + matrix() x {EvI,AvI,IvE,IvA,EvA,AvE}, scale+correctA, wall clock, host elevmask upload (34 MB, pageable) included",
+                "elevmask_resident": {"six_matrices_median_ms": medd, "min_ms": mnd, "what": "the same through ib_regrid_matrices_dev: elevmaskI already in HBM"}}
     guarded("build_greenland_1km", build_1km)
 
     # ---- Hntr at ETOPO1 scale (make_topoo / etopo1_ice.cpp:17-29): 21600x10800 -> 144x90 and 360x180
@@ -335,6 +340,14 @@ def more_single_gpu(torch, api, args, cfg, gcm, mats, X, YE, YA, stream, peak, n
         return res
     guarded("hntr_etopo1", hntr)
     return out
+
+
+def more_config5_n1(torch, api, args, dev):
+    """The N=1 point of the configs[4] strong-scaling build curve (same code path as N>1)."""
+    try:
+        return strong_scaling_build(torch, None, api, args, 1, 0, dev)
+    except Exception as e:
+        return {"error": str(e).splitlines()[0][:200]}
 
 
 def strong_scaling_build(torch, dist, api, args, world, rank, dev):
@@ -365,6 +378,7 @@ def strong_scaling_build(torch, dist, api, args, world, rank, dev):
             g.filter_cellsA(multi.partition_cellsA(sh.ex_ij[:, 0], gA.nA, world)[rank])
         nX_mine = g.nX(sh.name)
         del sh
+        em = torch.from_numpy(em).to(dev)       # the ice model's elevation / mask lives in HBM: no 288 MB upload per build
         if world > 1:
             dist.barrier()
         med, mn = timed_build(torch, g, shape, em, SIX, reps, scale=False, correctA=True)
@@ -373,7 +387,8 @@ def strong_scaling_build(torch, dist, api, args, world, rank, dev):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         out[shape] = {"six_matrices_ms_slowest_rank_median": float(t[0].item()), "nX": nX_full, "nX_largest_domain": int(t[1].item()), "ranks": world}
         del g, em
-    out["what"] = "strong scaling: every rank builds {EvI,AvI,IvE,IvA,EvA,AvE} (unscaled, correctA) for its GCM-cell domain of the sheet; rows of AvI/EvI of the domains are disjoint and concatenate (ib_w_combine_chunks)"
+    out["what"] = ("strong scaling: every rank builds {EvI,AvI,IvE,IvA,EvA,AvE} (unscaled, correctA) for its GCM-cell domain of the sheet, elevmaskI "
+                   "resident in HBM (ib_regrid_matrices_dev); rows of AvI/EvI of the domains are disjoint and concatenate (ib_w_combine_chunks)")
     return out
 
 
@@ -506,7 +521,10 @@ def run_b200(args):
 
     # CUDA graph of GSTEPS consecutive steps (launch-bound otherwise).  The library's launches (programmatic dependent
     # launches included) and its stream-ordered allocations are capturable.
-    GSTEPS = 8
+    # steps per captured graph: the largest divisor of `steps` in 8..64 (no eager remainder), else 16.  At N>1 a graph ends
+    # with the join of the last merges, so longer graphs expose that latency less often.
+    divs = [d for d in range(8, 65) if args.steps % d == 0]
+    GSTEPS = (max(divs) if world > 1 else min(divs)) if divs else 16
     graph, launches_per_graph = None, None
     # N>1 with the peer merge: nothing but the library's kernels is captured (no collective call), every rank captures the
     # same GSTEPS steps.  With NCCL inside the capture one rank falling back to eager while another replays would
@@ -578,6 +596,7 @@ def run_b200(args):
     more = None
     if world == 1 and not args.no_more:
         more = more_single_gpu(torch, api, args, cfg, gcm, mats, X, YE, YA, stream, peak, nrep_side)
+        more["build_config5_strong_scaling"] = more_config5_n1(torch, api, args, dev)
     if world > 1 and not args.no_more:
         try:
             more = {"build_config5_strong_scaling": strong_scaling_build(torch, dist, api, args, world, rank, dev)}

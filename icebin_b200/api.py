@@ -349,6 +349,16 @@ class GCMRegridder:
         check(lib().ib_regrid_matrices(self._h, ix, _p(em), int(scale), int(correctA), _p(sg), C.byref(h)))
         return RegridMatrices(h, self)
 
+    def regrid_matrices_dev(self, sheet_name, d_elevmask_ptr, scale=True, correctA=True, sigma=(0, 0, 0), stream=0):
+        """The same with elevmaskI [nI] fp64 already in device memory (the ice model's state stays in HBM): no upload."""
+        if sheet_name not in self.sheets:
+            raise KeyError(sheet_name)
+        sg = _c(sigma, np.float64)
+        h = vp()
+        check(lib().ib_regrid_matrices_dev(self._h, self.sheets[sheet_name], vp(d_elevmask_ptr), int(scale), int(correctA), _p(sg),
+                                           vp(stream) if stream else None, C.byref(h)))
+        return RegridMatrices(h, self)
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):

@@ -22,6 +22,7 @@
 // Spinning kernels of DIFFERENT ranks must run on different GPUs (nothing guarantees co-scheduling on one device).
 // On one GPU (tests), ranks are driven one after the other with ib_xchg_publish_dev / ib_xchg_gather_dev, so every
 // flag is already set when it is polled.
+#include <algorithm>
 #include <cstring>
 
 #include "types.cuh"
@@ -30,6 +31,7 @@ namespace ib {
 
 constexpr unsigned long long XCHG_TIMEOUT_NS = 4000000000ull;
 constexpr int XCHG_MAX_RANKS = 64;
+constexpr int XCHG_MAX_BLOCKS = 48;
 
 struct XHdr {
     unsigned long long ready, done;
@@ -132,18 +134,30 @@ __global__ void __launch_bounds__(256) xchg_publish_kernel(const XArgs a)
     double *buf = reinterpret_cast<double *>(base + sizeof(XHdr)) + (int64_t)(s & 1) * a.total * a.ldb;
     const int nv2 = (a.nvar + 1) / 2;
     const int64_t work = a.total * nv2;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t g = t / nv2;
-        const int f = (int)(t - g * nv2) * 2;
-        int p = 0;
-        while (p + 1 < a.nparts && g >= a.part[p + 1].off) ++p;
-        const XPartDev &P = a.part[p];
-        const int32_t r = P.loc[g - P.off];
-        if (r < 0) continue;                     // not mine: nobody reads this row of my buffer
-        const double *y = P.Y + (int64_t)r * P.ldy + f;
-        double2 v = make_double2(y[0], f + 1 < a.nvar ? y[1] : 0.0);
-        if (P.scaled) { const double w = P.wlocal[r]; v.x *= w; v.y *= w; }      // back to this sheet's unscaled sum
-        *reinterpret_cast<double2 *>(buf + g * a.ldb + f) = v;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < work; t0 += 4 * stride) {
+        double2 v[4];
+        double *dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                        // four independent loads in flight per thread
+            dst[u] = nullptr;
+            const int64_t t = t0 + u * stride;
+            if (t >= work) continue;
+            const int64_t g = t / nv2;
+            const int f = (int)(t - g * nv2) * 2;
+            int p = 0;
+            while (p + 1 < a.nparts && g >= a.part[p + 1].off) ++p;
+            const XPartDev &P = a.part[p];
+            const int32_t r = P.loc[g - P.off];
+            if (r < 0) continue;                             // not mine: nobody reads this row of my buffer
+            const double *y = P.Y + (int64_t)r * P.ldy + f;
+            v[u] = make_double2(y[0], f + 1 < a.nvar ? y[1] : 0.0);
+            if (P.scaled) { const double w = P.wlocal[r]; v[u].x *= w; v[u].y *= w; }      // back to this sheet's unscaled sum
+            dst[u] = buf + g * a.ldb + f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (dst[u]) *reinterpret_cast<double2 *>(dst[u]) = v[u];
     }
     __threadfence_system();
     __syncthreads();
@@ -188,11 +202,26 @@ __global__ void __launch_bounds__(256) xchg_gather_kernel(const XArgs a)
         double sc;
         if (k >= 0) {
             uint64_t own = P.owners[k];
+            const int64_t at = boff + (P.off + k) * a.ldb + f;
             v = make_double2(0.0, 0.0);
-            for (int r = 0; own; ++r, own >>= 1) {          // ascending rank order: every rank adds in the same order
-                if (!(own & 1)) continue;
-                const double2 c = ld_peer(reinterpret_cast<const double *>(a.peers[r]) + boff + (P.off + k) * a.ldb + f);
-                v.x += c.x; v.y += c.y;
+            while (own) {                                   // ascending rank order: every rank adds in the same order
+                // the loads of up to eight owners are independent of each other: one NVLink round trip for all of them
+                double2 c[8];
+                uint64_t rest = own;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    c[j] = make_double2(0.0, 0.0);
+                    if (rest) {
+                        const int r = __ffsll((long long)rest) - 1;
+                        rest &= rest - 1;
+                        c[j] = ld_peer(reinterpret_cast<const double *>(a.peers[r]) + at);
+                    }
+                }
+                uint64_t used = own;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (used) { used &= used - 1; v.x += c[j].x; v.y += c[j].y; }
+                own = rest;
             }
             sc = 1. / P.wtot[k];                            // to_dense: val * scaleE, scaleE = 1 / sum(weights)
         } else {
@@ -234,8 +263,9 @@ static XArgs make_args(Xchg &x, double *const *dY, const int64_t *ldy, int nvar)
 void xchg_publish(Xchg &x, double *const *dY, const int64_t *ldy, int nvar, cudaStream_t s)
 {
     XArgs a = make_args(x, dY, ldy, nvar);
+    // few blocks, several items per thread: the kernels usually run in the CTA slots a resident SpMM grid leaves free
     const int64_t work = std::max<int64_t>(1, x.total * ((nvar + 1) / 2));
-    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(work, 256), 2 * sm_count());
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(work, 256 * 4), XCHG_MAX_BLOCKS);
     xchg_publish_kernel<<<grid, 256, 0, s>>>(a);
     IB_LAUNCHED();
 }
@@ -245,7 +275,8 @@ void xchg_gather(Xchg &x, double *const *dY, const int64_t *ldy, int nvar, cudaS
     int64_t rows = 0;
     for (auto &P : x.parts) rows += P.scaled ? P.nshared : P.nrow;
     const int64_t work = std::max<int64_t>(1, rows * ((nvar + 1) / 2));
-    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(work, 256), 2 * sm_count());
+    const bool all_scaled = std::all_of(x.parts.begin(), x.parts.end(), [](XPart const &P) { return P.scaled != 0; });
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(work, 256 * 4), all_scaled ? XCHG_MAX_BLOCKS : 2 * sm_count());
     xchg_gather_kernel<<<grid, 256, 0, s>>>(a);
     IB_LAUNCHED();
 }
