@@ -20,6 +20,7 @@ UNITS = {
     "build.cu": ["-fmad=false"],
     "apply.cu": ["-fmad=false"],
     "apply_stream.cu": ["-fmad=false"],
+    "apply_group.cu": ["-fmad=false"],
     "smooth.cu": ["-fmad=false"],
     "couple.cu": ["-fmad=false"],
     "exgrid.cu": ["-fmad=false"],

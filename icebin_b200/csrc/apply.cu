@@ -756,7 +756,7 @@ static void compute_cons_v(Weighted &W, cudaStream_t s)
 
 static void wdot(const double *w, const double *A, int64_t lda, int64_t nrow, int nvar, DBuf<double> &part, int &nb, cudaStream_t s)
 {
-    nb = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(nrow, 64)), 4 * sm_count());
+    nb = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(nrow, 16)), 4 * sm_count());     // short row runs: many blocks, little latency each
     int64_t rpb = cdiv(std::max<int64_t>(nrow, 1), nb);
     nb = (int)cdiv(std::max<int64_t>(nrow, 1), rpb);
     part.alloc((size_t)nb * nvar, s);
@@ -874,6 +874,8 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         }
         return;
     }
+    // tall matrices with longer rows that share columns (sigma-smoothed IvE / IvA): register-blocked groups of 16 rows
+    if (g_tune.use_group && !P.gc && P.max_row_len <= 128 && apply_group(W, dX, ldx, nvar, dY, ldy, rlo, rhi, s)) return;
     // X-stationary path: tall matrix, few columns, no long rows
     if (vec2 && !ranged && W.ncol > 0 && W.nrow >= 8 * W.ncol && P.max_row_len <= 256 && nvar >= 8 && 2 * W.nnz >= 3 * W.nrow) {
         int F = 64;

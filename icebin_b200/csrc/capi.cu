@@ -196,6 +196,7 @@ int ib_tune(const char *key, int value)
     else if (k == "gc_nq") { if (value != 0 && value != 1 && value != 2 && value != 4) fail(IB_ERR_ARG, "ib_tune: gc_nq in {0,1,2,4}"); g_tune.gc_nq = value; }
     else if (k == "use_stream") g_tune.use_stream = value != 0;
     else if (k == "use_gc") g_tune.use_gc = value != 0;
+    else if (k == "use_group") g_tune.use_group = value != 0;
     else if (k == "hntr_generic") g_tune.hntr_generic = value != 0;
     else fail(IB_ERR_ARG, "ib_tune: unknown key '%s'", key);
     return IB_OK;

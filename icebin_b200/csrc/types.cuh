@@ -105,6 +105,14 @@ struct StreamPlan {
     DBuf<double> partials;      // [nslots][ldp]
 };
 
+// Register-blocked plan for tall matrices whose neighbouring rows share columns (apply_group.cu)
+struct GroupPlan {
+    bool tried = false, ok = false;
+    int64_t nitems = 0, nchunks = 0;
+    DBuf<int4> items;               // (first row, first chunk, end chunk, rows)
+    DBuf<unsigned char> chunks;     // chunk records: columns, presence masks, dense coefficient table
+};
+
 uint64_t next_uid();
 
 // linear::Weighted_Eigen: CSR matrix (rows = output space) + weights + dims.
@@ -120,6 +128,7 @@ struct Weighted {
     std::unique_ptr<Dim> owned[2];
     ApplyPlan plan;
     StreamPlan stream_plan;
+    GroupPlan group_plan;
     uint64_t uid = next_uid();   // identifies the matrix in plans that involve a partner
     cudaStream_t stream = nullptr;
 };
@@ -133,6 +142,8 @@ void smooth_rows(RegridMatrices &rm, Weighted &W, Params const &p);
 // apply.cu
 void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY, int64_t ldy, bool force_conservation,
                cudaStream_t s, int64_t row_begin = 0, int64_t row_end = -1);
+// apply_group.cu: tall matrices with ~16 nonzeros per row (sigma-smoothed IvE / IvA); false = does not fit
+bool apply_group(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY, int64_t ldy, int row_lo, int row_hi, cudaStream_t s);
 // apply_stream.cu: [Y1; Y2] = [M1; M2] X in one pass over X (M2 may be null); false = the pair does not qualify
 bool apply_stream(Weighted &M1, Weighted *M2, const double *dX, int64_t ldx, int nvar, double *dY1, int64_t ldy1, double *dY2,
                   int64_t ldy2, cudaStream_t s);

@@ -53,7 +53,7 @@ int ib_set_device(int device);
 int64_t ib_launch_count(void);
 /* Performance knobs; results never depend on them.  Keys: "stream_bps", "tma_bps" (CTAs per SM of the one-pass / ring
  * SpMM kernels, 1..8), "stream_spare" (CTA slots the one-pass kernel leaves free for a concurrent small kernel, 0..64), "gc_nq" (64-field groups per lane of the distinct-column kernel: 0 = by nvar, 1, 2, 4),
- * "use_stream", "use_gc" (0 = route around the one-pass kernel / the distinct-column kernel), "hntr_generic" (1 = Hntr
+ * "use_stream", "use_gc", "use_group" (0 = route around the one-pass / distinct-column / register-blocked group kernel), "hntr_generic" (1 = Hntr
  * always takes its generic kernels). */
 int ib_tune(const char *key, int value);
 /* Return the device memory the library's stream-ordered allocations cached (cudaMemPoolTrimTo); synchronises the device. */

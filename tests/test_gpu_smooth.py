@@ -68,3 +68,28 @@ def test_smoothing_with_identity_dimI(cfg1):
     r, c, v = csc_order(*Wg.to_coo_dense())
     assert np.array_equal(r, Wo.row) and np.array_equal(c, Wo.col)
     np.testing.assert_allclose(v, Wo.val, rtol=1e-12, atol=0)
+
+
+def test_smoothed_apply_nan_reaches_only_named_rows(cfg2):
+    """The register-blocked group kernel keeps a dense coefficient table with zeros for the rows that do not name a column;
+    a NaN in X must still reach exactly the rows whose neighbourhood names that E cell (structural zeros are not multiplied)."""
+    import scipy.sparse as sp
+    gg = make_gpu(cfg2)
+    em = cfg2["elevmask"][0]
+    Wg = gg.regrid_matrices(cfg2["sheets"][0].name, em, scale=True, correctA=True, sigma=(50e3, 50e3, 100.0)).matrix("IvE")
+    r, c, v = Wg.to_coo_dense()
+    M = sp.csr_matrix((v, (r, c)), shape=Wg.shape)
+    X = np.random.default_rng(3).uniform(0, 1, (64, Wg.shape[1]))
+    bad = [5, 400, Wg.shape[1] - 1]
+    X[7, bad] = np.nan
+    X[9, bad[0]] = np.inf
+    Y = Wg.apply(X, force_conservation=False)
+    hit = np.zeros(Wg.shape[0], bool)
+    hit[M.tocsc()[:, bad].tocoo().row] = True
+    assert np.array_equal(np.isnan(Y[7]), hit)
+    hit0 = np.zeros(Wg.shape[0], bool)
+    hit0[M.tocsc()[:, [bad[0]]].tocoo().row] = True
+    assert np.array_equal(~np.isfinite(Y[9]), hit0)
+    ok = np.ones(64, bool); ok[[7, 9]] = False
+    Xc = X.copy(); Xc[7, bad] = 0.5; Xc[9, bad[0]] = 0.5
+    np.testing.assert_allclose(Y[ok], (M @ Xc[ok].T).T, rtol=1e-12, atol=0)

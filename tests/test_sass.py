@@ -32,7 +32,7 @@ def apply_sass():
     from icebin_b200 import build
     build.build()
     outs, funcs = "", {}
-    for unit in ("apply.o", "apply_stream.o"):
+    for unit in ("apply.o", "apply_stream.o", "apply_group.o"):
         obj = os.path.join(ROOT, "icebin_b200", "build", unit)
         if not os.path.exists(obj):
             pytest.skip("object files not kept")
@@ -48,7 +48,7 @@ def test_only_sm100a_code(apply_sass):
     assert archs == {"sm_100a"}, archs
 
 
-@pytest.mark.parametrize("kernel", ["spmm_gc_kernel", "spmm_tma_kernel", "spmm_stream_kernel"])
+@pytest.mark.parametrize("kernel", ["spmm_gc_kernel", "spmm_tma_kernel", "spmm_stream_kernel", "smooth_group_kernel"])
 def test_bulk_async_copies_and_mbarriers(apply_sass, kernel):
     _, funcs = apply_sass
     mine = {k: v for k, v in funcs.items() if kernel in k}
