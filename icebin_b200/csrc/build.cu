@@ -269,6 +269,43 @@ struct K1Emit {
     }
 };
 
+// Is the emitted stream already ordered by its row part / its column part?  (Dense ids of a fresh ice-grid dim are ranks
+// of first appearance in this very stream, so with an ice-cell-major exchange grid the I side comes out sorted.)
+// flags: bit 0 column parts non-decreasing, bit 1 row parts non-decreasing, bit 2 no run of more than LOCAL_SORT_MAX equal rows
+constexpr int LOCAL_SORT_MAX = 32;
+__global__ void order_check_kernel(const uint64_t *keys, int64_t n, int cbits, int *flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || i == 0) return;
+    const uint64_t cm = (uint64_t(1) << cbits) - 1;
+    const uint64_t k = keys[i], p = keys[i - 1];
+    int clear = 0;
+    if ((k & cm) < (p & cm)) clear |= 1;
+    if ((k >> cbits) < (p >> cbits)) clear |= 2;
+    if (i >= LOCAL_SORT_MAX && (keys[i - LOCAL_SORT_MAX] >> cbits) == (k >> cbits)) clear |= 4;
+    if (clear) atomicAnd(flags, ~clear);
+}
+// Rows already contiguous and in order: each row's few entries are put in column order by one thread (stable: equal
+// keys keep their emission order, in which they are summed later)
+__global__ void local_sort_kernel(const uint64_t *kin, const double *vin, int64_t n, int cbits, uint64_t *kout, double *vout)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t r = kin[i] >> cbits;
+    if (i > 0 && (kin[i - 1] >> cbits) == r) return;        // not the head of its row
+    uint64_t k[LOCAL_SORT_MAX];
+    double v[LOCAL_SORT_MAX];
+    int m = 0;
+    for (int64_t j = i; j < n && m < LOCAL_SORT_MAX && (kin[j] >> cbits) == r; ++j, ++m) {
+        const uint64_t kk = kin[j];
+        const double vv = vin[j];
+        int q = m;
+        while (q > 0 && k[q - 1] > kk) { k[q] = k[q - 1]; v[q] = v[q - 1]; --q; }
+        k[q] = kk; v[q] = vv;
+    }
+    for (int q = 0; q < m; ++q) { kout[i + q] = k[q]; vout[i + q] = v[q]; }
+}
+
 __global__ void gather_i32_kernel(const uint32_t *perm, const int32_t *src, int64_t n, int32_t *dst)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -496,8 +533,28 @@ std::unique_ptr<Weighted> build_matrix(RegridMatrices &rm, std::string const &sp
     d0->dense_extent = nrow;
     d1->dense_extent = ncol;
 
-    // ---- K2: sort + reduce-by-key -> COO sorted by (row, col)
-    int which = radix_sort_pairs<uint64_t, double>(k0.p, v0.p, k1.p, v1.p, ntrip, c.cbits + rbits, s);
+    // ---- K2: sort + reduce-by-key -> COO sorted by (row, col).  The stream often arrives half sorted: ordered by ice
+    // cell (the exchange grid is ice-cell-major and the ice dim is fresh) -- then a few radix passes or none are needed
+    int order = 0;
+    if (ntrip > 1) {
+        DBuf<int> oflags(1, s);
+        const int all = 7;
+        IB_CUDA(cudaMemcpyAsync(oflags.p, &all, sizeof all, cudaMemcpyHostToDevice, s));
+        order_check_kernel<<<(unsigned)cdiv(ntrip, 256), 256, 0, s>>>(k0.p, ntrip, c.cbits, oflags.p);
+        IB_LAUNCHED();
+        oflags.download(&order, 1);
+        IB_CUDA(cudaStreamSynchronize(s));
+    }
+    int which;
+    if ((order & 6) == 6) {                 // rows in order, short rows: one local sort per row, no radix pass
+        local_sort_kernel<<<(unsigned)cdiv(ntrip, 256), 256, 0, s>>>(k0.p, v0.p, ntrip, c.cbits, k1.p, v1.p);
+        IB_LAUNCHED();
+        which = 1;
+    } else if (order & 1) {                 // columns in order: a stable sort on the row bits alone
+        which = radix_sort_pairs<uint64_t, double>(k0.p, v0.p, k1.p, v1.p, ntrip, c.cbits + rbits, s, c.cbits);
+    } else {
+        which = radix_sort_pairs<uint64_t, double>(k0.p, v0.p, k1.p, v1.p, ntrip, c.cbits + rbits, s);
+    }
     const uint64_t *sk = which ? k1.p : k0.p;
     const double *sv = which ? v1.p : v0.p;
 
@@ -522,9 +579,8 @@ std::unique_ptr<Weighted> build_matrix(RegridMatrices &rm, std::string const &sp
     if (nnz > 0) {
         DBuf<int32_t> segstart((size_t)nnz + 1, s);
         scan_apply<uint32_t>(hs, HeadLoad<uint64_t>{sk}, AddU32{}, 0u, ReduceApply{sk, c.cbits, row.p, W->col.p, segstart.p}, s);
-        const int32_t ntrip32 = (int32_t)ntrip;
-        IB_CUDA(cudaMemcpyAsync(segstart.p + nnz, &ntrip32, sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        IB_CUDA(cudaStreamSynchronize(s));
+        fill_i32_kernel<<<1, 32, 0, s>>>(segstart.p + nnz, 1, (int32_t)ntrip);      // sentinel (no host copy, no sync)
+        IB_LAUNCHED();
         seg_sum(segstart.p, nullptr, sv, nnz, W->val.p, s);      // duplicate (row, col) triplets summed in emission order
         seg_ptr_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(row.p, nnz, nrow, W->rowptr.p);
         IB_LAUNCHED();

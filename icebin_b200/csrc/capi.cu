@@ -32,7 +32,7 @@ int device_index()
     return dev;
 }
 
-// Freed blocks stay in the device's default memory pool up to 1/8 of the device's memory (steady-state matrix builds --
+// Freed blocks stay in the device's default memory pool up to 1/4 of the device's memory (steady-state matrix builds --
 // ~10 GB of temporaries for a 36 M-cell sheet -- then never reach the driver allocator); what exceeds it goes back to the
 // driver at the next synchronisation, so a co-resident allocator (the host application's) is not starved.  ib_trim()
 // releases everything.
@@ -40,7 +40,7 @@ static uint64_t pool_keep_bytes()
 {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return 4ull << 30; }
-    return std::max<uint64_t>(4ull << 30, tot / 8);
+    return std::max<uint64_t>(4ull << 30, tot / 4);
 }
 
 cudaStream_t default_stream()

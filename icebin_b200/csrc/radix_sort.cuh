@@ -92,6 +92,44 @@ __global__ void __launch_bounds__(RS_BLOCK) rs_scatter_kernel(const K *__restric
     }
 }
 
+// Exclusive scan of a small [digit][tile] table in ONE block (replaces three launches of the general scan when the table
+// has at most RS_SMALL entries: sorts of up to ~0.5 M records)
+constexpr int RS_SMALL_BLOCK = 1024;
+constexpr int RS_SMALL = RS_SMALL_BLOCK * 64;
+__global__ void __launch_bounds__(RS_SMALL_BLOCK) rs_scan_small_kernel(uint32_t *hist, int n)
+{
+    __shared__ uint32_t wsum[RS_SMALL_BLOCK / 32];
+    const int per = (n + RS_SMALL_BLOCK - 1) / RS_SMALL_BLOCK;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    uint32_t s = 0;
+    for (int i = b; i < e; ++i) s += hist[i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wsum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += o;
+        }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    uint32_t run = inc - s + (warp ? wsum[warp - 1] : 0u);
+    for (int i = b; i < e; ++i) {
+        const uint32_t c = hist[i];
+        hist[i] = run;
+        run += c;
+    }
+}
+
 struct U32Load {
     const uint32_t *p;
     __device__ uint32_t operator()(int64_t i) const { return p[i]; }
@@ -104,8 +142,11 @@ struct U32Store {
 // Sorts n records by the low `keybits` bits of the key.  (k0,v0) hold the input; (k1,v1) are scratch of the
 // same size.  Returns 0 if the sorted data ends in (k0,v0), 1 if in (k1,v1).
 template <class K, class V>
-int radix_sort_pairs(K *k0, V *v0, K *k1, V *v1, int64_t n, int keybits, cudaStream_t s)
+int radix_sort_pairs(K *k0, V *v0, K *k1, V *v1, int64_t n, int keybits, cudaStream_t s, int first_bit = 0)
 {
+    // first_bit > 0: the input is already ordered by the low `first_bit` bits; only the bits above them are sorted on
+    // (a stable sort by the high bits of a stream sorted by the low bits is sorted by the whole key)
+    keybits -= first_bit;
     if (n <= 1 || keybits <= 0) return 0;
     if (n >= (int64_t(1) << 32)) fail(IB_ERR_ARG, "radix_sort_pairs: n too large");
     int passes = (keybits + 7) / 8;
@@ -116,11 +157,16 @@ int radix_sort_pairs(K *k0, V *v0, K *k1, V *v1, int64_t n, int keybits, cudaStr
     for (int p = 0; p < passes; ++p) {
         K *ki = cur ? k1 : k0, *ko = cur ? k0 : k1;
         V *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
-        rs_hist_kernel<K><<<ntiles, RS_BLOCK, 0, s>>>(ki, n, p * 8, hist.p, ntiles);
+        rs_hist_kernel<K><<<ntiles, RS_BLOCK, 0, s>>>(ki, n, first_bit + p * 8, hist.p, ntiles);
         IB_LAUNCHED();
-        transform_scan<uint32_t>(st, (int64_t)RS_RADIX * ntiles, U32Load{hist.p}, AddU32{}, 0u, s);
-        scan_apply<uint32_t>(st, U32Load{hist.p}, AddU32{}, 0u, U32Store{hist.p}, s);
-        rs_scatter_kernel<K, V><<<ntiles, RS_BLOCK, 0, s>>>(ki, vi, ko, vo, n, p * 8, hist.p, ntiles);
+        if ((int64_t)RS_RADIX * ntiles <= RS_SMALL) {
+            rs_scan_small_kernel<<<1, RS_SMALL_BLOCK, 0, s>>>(hist.p, RS_RADIX * ntiles);
+            IB_LAUNCHED();
+        } else {
+            transform_scan<uint32_t>(st, (int64_t)RS_RADIX * ntiles, U32Load{hist.p}, AddU32{}, 0u, s);
+            scan_apply<uint32_t>(st, U32Load{hist.p}, AddU32{}, 0u, U32Store{hist.p}, s);
+        }
+        rs_scatter_kernel<K, V><<<ntiles, RS_BLOCK, 0, s>>>(ki, vi, ko, vo, n, first_bit + p * 8, hist.p, ntiles);
         IB_LAUNCHED();
         cur ^= 1;
     }

@@ -31,8 +31,9 @@ struct ReduceApply {
 // Segments of <= SEG_SEQ elements are summed sequentially by one thread, in storage order -- the order in which Eigen
 // sums duplicate triplets and ibmisc's sum() walks a matrix, so those results are bit-identical to the oracle.
 // Longer segments (EvA/AvE: thousands of exchange cells per (E, A) pair; A-grid weights at 1 km) would serialise one
-// thread for milliseconds; they are queued and reduced by one warp each: lane-strided partial sums followed by a
-// fixed butterfly, i.e. deterministic, differing from the sequential order only in association (<= 1e-13 relative).
+// thread for milliseconds; they are queued and reduced by one CTA each: thread-strided partial sums followed by a
+// fixed butterfly and a fixed order over the warps, i.e. deterministic, differing from the sequential order only in
+// association (<= 1e-13 relative).
 constexpr int SEG_SEQ = 64;
 static __global__ void seg_sum_short_kernel(const int32_t *__restrict__ ptr, const uint32_t *__restrict__ perm, const double *__restrict__ val,
                                      int64_t nseg, double *__restrict__ out, int32_t *__restrict__ long_list, int *__restrict__ nlong)
@@ -46,22 +47,32 @@ static __global__ void seg_sum_short_kernel(const int32_t *__restrict__ ptr, con
     else for (int32_t j = b; j < e; ++j) s += val[j];
     out[g] = s;
 }
+// one CTA per long segment (the A-grid rows at 1 km hold ~17 k entries each, EvA / AvE thousands of duplicates per entry):
+// thread-strided partial sums, then a fixed butterfly inside each warp and a fixed order over the warps
 static __global__ void __launch_bounds__(256) seg_sum_long_kernel(const int32_t *__restrict__ ptr, const uint32_t *__restrict__ perm,
                                                            const double *__restrict__ val, double *__restrict__ out,
                                                            const int32_t *__restrict__ long_list, const int *__restrict__ nlong)
 {
-    const int lane = threadIdx.x & 31;
-    const int nw = (gridDim.x * blockDim.x) >> 5;
+    __shared__ double wsum[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = *nlong;
-    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nw) {
+    for (int w = blockIdx.x; w < n; w += gridDim.x) {
         const int32_t g = long_list[w];
         const int32_t b = ptr[g], e = ptr[g + 1];
         double s = 0;
-        if (perm) for (int32_t j = b + lane; j < e; j += 32) s += val[perm[j]];
-        else for (int32_t j = b + lane; j < e; j += 32) s += val[j];
+        if (perm) for (int32_t j = b + threadIdx.x; j < e; j += 256) s += val[perm[j]];
+        else for (int32_t j = b + threadIdx.x; j < e; j += 256) s += val[j];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) out[g] = s;
+        if (lane == 0) wsum[warp] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = wsum[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) t += wsum[k];
+            out[g] = t;
+        }
+        __syncthreads();
     }
 }
 static void seg_sum(const int32_t *ptr, const uint32_t *perm, const double *val, int64_t nseg, double *out, cudaStream_t s)
