@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(RS_BLOCK) rs_scatter_kernel(const K *__restric
 // has at most RS_SMALL entries: sorts of up to ~0.5 M records)
 constexpr int RS_SMALL_BLOCK = 1024;
 constexpr int RS_SMALL = RS_SMALL_BLOCK * 64;
-__global__ void __launch_bounds__(RS_SMALL_BLOCK) rs_scan_small_kernel(uint32_t *hist, int n)
+static __global__ void __launch_bounds__(RS_SMALL_BLOCK) rs_scan_small_kernel(uint32_t *hist, int n)
 {
     __shared__ uint32_t wsum[RS_SMALL_BLOCK / 32];
     const int per = (n + RS_SMALL_BLOCK - 1) / RS_SMALL_BLOCK;
