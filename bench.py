@@ -459,13 +459,14 @@ def run_b200(args):
             rm_u = gcm.regrid_matrices(sh.name, em_host, scale=False, correctA=True)
             EvI, AvI = rm_u.matrix("EvI"), rm_u.matrix("AvI")
             assert (EvI.shape, AvI.shape) == ((nE_d, nI_d), (nA_d, nI_d))
-            merges = [multi.SheetMerge([(gcm.nE, EvI), (gcm.nA, AvI)], nvar, dev) for _ in range(2)]
+            merges = [multi.SheetMerge([(gcm.nE, EvI), (gcm.nA, AvI)], nvar, dev) for _ in range(4)]
             mergeA = merges[0]
         side = torch.cuda.Stream(device=dev, priority=-1)       # the small merge kernels go first when a CTA slot frees up
-        YEs = [YE, torch.empty_like(YE)]
-        YAs = [YA, torch.empty_like(YA)]
-        spmm_done = [torch.cuda.Event() for _ in range(2)]
-        merge_done = [torch.cuda.Event() for _ in range(2)]
+        NBUF = 4            # result buffer sets: a merge may lag its SpMM by NBUF - 1 steps (absorbs the ranks' jitter)
+        YEs = [YE] + [torch.empty_like(YE) for _ in range(NBUF - 1)]
+        YAs = [YA] + [torch.empty_like(YA) for _ in range(NBUF - 1)]
+        spmm_done = [torch.cuda.Event() for _ in range(NBUF)]
+        merge_done = [torch.cuda.Event() for _ in range(NBUF)]
 
     YE_p, YA_p = YE.data_ptr(), YA.data_ptr()
     # pre-built argument arrays for the C ABI (the per-step Python cost matters at a 60 us step)
@@ -475,14 +476,14 @@ def run_b200(args):
     _ld2 = (C.c_int64 * 2)(nvar, nvar)
     _Yp = [(_vp * 2)(YE_p, YA_p)]
     if mergeA is not None:
-        _Yp = [(_vp * 2)(YEs[k].data_ptr(), YAs[k].data_ptr()) for k in range(2)]
+        _Yp = [(_vp * 2)(YEs[k].data_ptr(), YAs[k].data_ptr()) for k in range(NBUF)]
     _apply_many = lib().ib_w_apply_many_dev
     _X, _st = _vp(X.data_ptr()), _vp(stream)
     if mergeA is not None and args.merge == "peer":
-        _pa = [peer.args([YEs[k], YAs[k]]) for k in range(2)]
+        _pa = [peer.args([YEs[k], YAs[k]]) for k in range(NBUF)]
         _side = _vp(side.cuda_stream)
     step_no = [0]
-    fresh = [True, True]       # no exchange pending on buffer set k (start of the run / of a captured graph)
+    fresh = [True] * 8         # no exchange pending on buffer set k (start of the run / of a captured graph)
 
     def step():
         # EvI and AvI act on the same ice-grid fields (IceCoupler.cpp:445-446): one call; the library applies the
@@ -490,7 +491,7 @@ def run_b200(args):
         if mergeA is None:
             check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[0], _ld2, 1, _st))
             return
-        k = step_no[0] & 1
+        k = step_no[0] % NBUF
         step_no[0] += 1
         if not fresh[k]:
             tstream.wait_event(merge_done[k])             # buffers k are free again

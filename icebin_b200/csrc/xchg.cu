@@ -4,18 +4,23 @@
 // (IceCoupler.cpp:445-457); the GCM root gathers them with MPI (modele/GCMCoupler_ModelE.cpp:761-793) and
 // VectorMultivec::to_dense_scale / to_dense (multivec.cpp:35-81) sums them and divides by the summed weights.
 // Here one rank = one process = one GPU = one sheet, results stay in HBM, and only the cells that more than one sheet
-// touches travel: a rank PUBLISHES the rows of its shared cells in a buffer of its own memory that the peers have mapped
-// (CUDA IPC), and GATHERS, for each shared cell it holds, the owners' rows with plain loads over NVLink, added in
-// ascending rank order (every rank computes the same bits), times 1 / (summed weights).  No NCCL call, no host
-// round trip: two kernels per step, capturable in a CUDA graph, 4 KB per (cell, owner) at 512 fields instead of an
-// all-reduce of every shared row through every rank.
+// touches travel: a rank PUBLISHES its row of every shared cell by storing it straight into the inbox of the cell's other
+// owners (their memory is mapped with CUDA IPC; posted stores over NVLink), and GATHERS, for each shared cell it holds,
+// its own row and the rows in its inbox, added in ascending rank order (every rank computes the same bits), times
+// 1 / (summed weights).  No NCCL call, no host round trip: two small kernels per step, capturable in a CUDA graph,
+// 4 KB per (cell, other owner) at 512 fields instead of an all-reduce of every shared row through every rank.
 //
-// Protocol (all flags live in the WRITER's memory; readers poll them remotely):
-//   hdr.ready = t  : the rows of steps < t are published          (written by the last block of the publish kernel)
-//   hdr.done  = t  : this rank has finished gathering steps < t   (written by the last block of the gather kernel)
-//   publish(step s) reuses buffer s & 1, last read by the peers in step s - 2: it waits for done >= s - 1 on every peer
-//   that reads this rank, then packs, fences (system scope) and sets ready = s + 1;
-//   gather(step s) waits for ready >= s + 1 on every peer it reads, then loads.
+// Protocol (PUSH: data and flags travel as posted stores over NVLink; every wait polls LOCAL memory, so no rank ever
+// pays a load round trip over the link).  Rank r's region holds, for every peer q, an inbox [2 parities][shared rows] and
+// two counters:
+//   ready[q] = t : q has delivered its rows of steps < t into r's inbox        (stored remotely by q's publish kernel)
+//   done[q]  = t : q has finished gathering steps < t out of ITS inbox, i.e. r may overwrite q's inbox parity again
+//                                                                               (stored remotely by q's gather kernel)
+//   publish(step s): wait for done[q] >= s - 1 of every peer q that shares a cell (inbox parity s & 1 was last read in
+//   step s - 2), store this rank's row of every shared cell into the inbox of every other owner, fence (system scope),
+//   then set ready[me] = s + 1 in those peers;
+//   gather(step s): wait for ready[q] >= s + 1 of those peers, add own row and inbox rows in ascending rank order, scale;
+//   then set done[me] = s + 1 in the peers.
 // The step counter lives in device memory and is advanced by the gather kernel, so a captured graph replays.  Waits
 // give up after XCHG_TIMEOUT_NS (a dead peer must not hang the GPU); ib_xchg_status() reports it.
 //
@@ -34,10 +39,9 @@ constexpr int XCHG_MAX_RANKS = 64;
 constexpr int XCHG_MAX_BLOCKS = 48;
 
 struct XHdr {
-    unsigned long long ready, done;
-    unsigned long long pad[14];
+    unsigned long long ready[XCHG_MAX_RANKS], done[XCHG_MAX_RANKS];
 };
-static_assert(sizeof(XHdr) == 128, "header is one 128-byte line");
+static_assert(sizeof(XHdr) == 1024, "header: two counters per peer");
 
 struct XPart {
     int64_t nrow = 0, nshared = 0, off = 0;      // off: first row of the part in the exchange buffer
@@ -52,7 +56,7 @@ struct Xchg {
     int rank = 0, nranks = 1, device = 0;
     int64_t total = 0, ldb = 0;
     std::vector<XPart> parts;
-    void *region = nullptr;                 // XHdr + buf[2][total][ldb], cudaMalloc (IPC-exportable)
+    void *region = nullptr;                 // XHdr + inbox[2][nranks][total][ldb], cudaMalloc (IPC-exportable)
     size_t region_bytes = 0;
     void *peer[XCHG_MAX_RANKS] = {};        // mapped regions (peer[rank] = region)
     bool ipc_opened[XCHG_MAX_RANKS] = {};
@@ -87,17 +91,17 @@ __device__ __forceinline__ unsigned long long xtime()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// thread 0 of the block polls `field` (0 ready, 1 done) of every rank in `mask` until it reaches `want`
-__device__ void xchg_wait(const unsigned long long *peers, uint64_t mask, int field, unsigned long long want, int *err)
+// thread 0 of the block polls, in THIS rank's header, counter `field` (0 ready, 1 done) of every peer in `mask`
+__device__ void xchg_wait(const XHdr *mine, uint64_t mask, int field, unsigned long long want, int *err)
 {
     if (threadIdx.x == 0) {
         const unsigned long long t0 = xtime();
         for (int r = 0; r < XCHG_MAX_RANKS && (mask >> r); ++r) {
             if (!((mask >> r) & 1)) continue;
-            const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(peers[r]) + field;
+            const unsigned long long *flag = (field ? mine->done : mine->ready) + r;
             while (ld_acquire_sys(flag) < want) {
                 if (xtime() - t0 > XCHG_TIMEOUT_NS) { atomicExch(err, 1); break; }
-                __nanosleep(200);
+                __nanosleep(100);
             }
         }
     }
@@ -116,7 +120,7 @@ struct XPartDev {
 constexpr int XCHG_MAX_PARTS = 4;
 struct XArgs {
     XPartDev part[XCHG_MAX_PARTS];
-    int nparts, rank, nvar;
+    int nparts, rank, nranks, nvar;
     int64_t total, ldb;
     const unsigned long long *peers;        // [nranks] region addresses
     uint64_t reads_mask, readers_mask;
@@ -125,22 +129,28 @@ struct XArgs {
     int *err;
 };
 
-// one thread per (shared cell of any part, field pair)
+__device__ __forceinline__ double *xchg_inbox(unsigned long long region, int parity, int nranks, int from, int64_t total, int64_t ldb)
+{
+    return reinterpret_cast<double *>(region + sizeof(XHdr)) + ((int64_t)parity * nranks + from) * total * ldb;
+}
+
+// one thread per (shared cell of any part, field pair), four items in flight per thread: this rank's row of the cell
+// is stored into the inbox of every other owner
 __global__ void __launch_bounds__(256) xchg_publish_kernel(const XArgs a)
 {
     const unsigned long long s = *a.step;
-    if (s >= 2) xchg_wait(a.peers, a.readers_mask, 1, s - 1, a.err);      // the peers have finished reading buffer s & 1
-    unsigned char *base = reinterpret_cast<unsigned char *>(a.peers[a.rank]);
-    double *buf = reinterpret_cast<double *>(base + sizeof(XHdr)) + (int64_t)(s & 1) * a.total * a.ldb;
+    XHdr *mine = reinterpret_cast<XHdr *>(a.peers[a.rank]);
+    if (s >= 2) xchg_wait(mine, a.readers_mask, 1, s - 1, a.err);      // the peers have finished reading parity s & 1
     const int nv2 = (a.nvar + 1) / 2;
     const int64_t work = a.total * nv2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < work; t0 += 4 * stride) {
         double2 v[4];
-        double *dst[4];
+        uint64_t own[4];
+        int64_t at[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {                        // four independent loads in flight per thread
-            dst[u] = nullptr;
+            own[u] = 0;
             const int64_t t = t0 + u * stride;
             if (t >= work) continue;
             const int64_t g = t / nv2;
@@ -149,38 +159,48 @@ __global__ void __launch_bounds__(256) xchg_publish_kernel(const XArgs a)
             while (p + 1 < a.nparts && g >= a.part[p + 1].off) ++p;
             const XPartDev &P = a.part[p];
             const int32_t r = P.loc[g - P.off];
-            if (r < 0) continue;                             // not mine: nobody reads this row of my buffer
+            if (r < 0) continue;                             // not one of my cells
             const double *y = P.Y + (int64_t)r * P.ldy + f;
             v[u] = make_double2(y[0], f + 1 < a.nvar ? y[1] : 0.0);
             if (P.scaled) { const double w = P.wlocal[r]; v[u].x *= w; v[u].y *= w; }      // back to this sheet's unscaled sum
-            dst[u] = buf + g * a.ldb + f;
+            own[u] = P.owners[g - P.off] & ~(uint64_t(1) << a.rank);
+            at[u] = g * a.ldb + f;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-            if (dst[u]) *reinterpret_cast<double2 *>(dst[u]) = v[u];
+            for (uint64_t o = own[u]; o; o &= o - 1) {       // posted stores over NVLink
+                const int q = __ffsll((long long)o) - 1;
+                *reinterpret_cast<double2 *>(xchg_inbox(a.peers[q], (int)(s & 1), a.nranks, a.rank, a.total, a.ldb) + at[u]) = v[u];
+            }
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(a.counters, 1u) == gridDim.x - 1) {
         a.counters[0] = 0;
         __threadfence_system();
-        st_release_sys(reinterpret_cast<unsigned long long *>(base), s + 1);      // hdr.ready
+        for (uint64_t o = a.readers_mask; o; o &= o - 1) {
+            const int q = __ffsll((long long)o) - 1;
+            st_release_sys(reinterpret_cast<XHdr *>(a.peers[q])->ready + a.rank, s + 1);
+        }
     }
 }
 
-// one thread per (local row of any part, field pair): shared rows gather their owners' rows over NVLink, the others
-// are divided by their own weight
+// one thread per (cell, field pair): a shared cell's value is the sum over its owners, in ascending rank order, of this
+// rank's own row and the rows in its inbox (all local memory), times 1 / (summed weights); unscaled parts also divide
+// the rows of unshared cells by their own weight
 __global__ void __launch_bounds__(256) xchg_gather_kernel(const XArgs a)
 {
     const unsigned long long s = *a.step;
-    xchg_wait(a.peers, a.reads_mask, 0, s + 1, a.err);
+    XHdr *mine = reinterpret_cast<XHdr *>(a.peers[a.rank]);
+    xchg_wait(mine, a.reads_mask, 0, s + 1, a.err);
     const int nv2 = (a.nvar + 1) / 2;
     // work items: every local row of an unscaled part, only the shared cells of a scaled part
     int64_t cum[XCHG_MAX_PARTS + 1];
     cum[0] = 0;
     for (int p = 0; p < a.nparts; ++p) cum[p + 1] = cum[p] + (a.part[p].scaled ? a.part[p].nshared : a.part[p].nrow);
     const int64_t work = cum[a.nparts] * nv2;
-    const int64_t boff = sizeof(XHdr) / sizeof(double) + (int64_t)(s & 1) * a.total * a.ldb;
+    const double *inbox0 = xchg_inbox(a.peers[a.rank], (int)(s & 1), a.nranks, 0, a.total, a.ldb);
+    const int64_t per_rank = a.total * a.ldb;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t g = t / nv2;
         const int f = (int)(t - g * nv2) * 2;
@@ -198,34 +218,20 @@ __global__ void __launch_bounds__(256) xchg_gather_kernel(const XArgs a)
             k = P.slot[g];
         }
         double *y = P.Y + g * P.ldy + f;
-        double2 v;
+        double2 v = make_double2(y[0], f + 1 < a.nvar ? y[1] : 0.0);
         double sc;
         if (k >= 0) {
-            uint64_t own = P.owners[k];
-            const int64_t at = boff + (P.off + k) * a.ldb + f;
+            if (P.scaled) { const double w = P.wlocal[g]; v.x *= w; v.y *= w; }
+            const double2 own = v;
+            const int64_t at = (P.off + k) * a.ldb + f;
             v = make_double2(0.0, 0.0);
-            while (own) {                                   // ascending rank order: every rank adds in the same order
-                // the loads of up to eight owners are independent of each other: one NVLink round trip for all of them
-                double2 c[8];
-                uint64_t rest = own;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    c[j] = make_double2(0.0, 0.0);
-                    if (rest) {
-                        const int r = __ffsll((long long)rest) - 1;
-                        rest &= rest - 1;
-                        c[j] = ld_peer(reinterpret_cast<const double *>(a.peers[r]) + at);
-                    }
-                }
-                uint64_t used = own;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (used) { used &= used - 1; v.x += c[j].x; v.y += c[j].y; }
-                own = rest;
+            for (uint64_t o = P.owners[k]; o; o &= o - 1) {  // ascending rank order: every owner adds in the same order
+                const int q = __ffsll((long long)o) - 1;
+                const double2 c = q == a.rank ? own : ld_peer(inbox0 + q * per_rank + at);
+                v.x += c.x; v.y += c.y;
             }
             sc = 1. / P.wtot[k];                            // to_dense: val * scaleE, scaleE = 1 / sum(weights)
         } else {
-            v = make_double2(y[0], f + 1 < a.nvar ? y[1] : 0.0);
             sc = 1. / P.wlocal[g];
         }
         y[0] = v.x * sc;
@@ -235,8 +241,10 @@ __global__ void __launch_bounds__(256) xchg_gather_kernel(const XArgs a)
     if (threadIdx.x == 0 && atomicAdd(a.counters + 1, 1u) == gridDim.x - 1) {
         a.counters[1] = 0;
         __threadfence_system();
-        unsigned char *base = reinterpret_cast<unsigned char *>(a.peers[a.rank]);
-        st_release_sys(reinterpret_cast<unsigned long long *>(base) + 1, s + 1);  // hdr.done
+        for (uint64_t o = a.reads_mask; o; o &= o - 1) {
+            const int q = __ffsll((long long)o) - 1;
+            st_release_sys(reinterpret_cast<XHdr *>(a.peers[q])->done + a.rank, s + 1);
+        }
         *a.step = s + 1;
     }
 }
@@ -246,7 +254,7 @@ static XArgs make_args(Xchg &x, double *const *dY, const int64_t *ldy, int nvar)
     if (!x.connected) fail(IB_ERR_ARG, "ib_xchg: not connected (call ib_xchg_open or ib_xchg_open_local first)");
     if (nvar <= 0 || nvar > x.ldb) fail(IB_ERR_ARG, "ib_xchg: nvar %d exceeds the %ld fields the context was created for", nvar, (long)x.ldb);
     XArgs a{};
-    a.nparts = (int)x.parts.size(); a.rank = x.rank; a.nvar = nvar; a.total = x.total; a.ldb = x.ldb;
+    a.nparts = (int)x.parts.size(); a.rank = x.rank; a.nranks = x.nranks; a.nvar = nvar; a.total = x.total; a.ldb = x.ldb;
     for (int p = 0; p < a.nparts; ++p) {
         XPart &P = x.parts[p];
         if (P.nrow > 0 && !P.slot.p) fail(IB_ERR_ARG, "ib_xchg: part %d has no plan (ib_xchg_set_part)", p);
@@ -311,7 +319,7 @@ int ib_xchg_create(ib_xchg **out, int rank, int nranks, int nparts, const int64_
         x.parts[p].off = x.total;
         x.total += nshared[p];
     }
-    x.region_bytes = sizeof(XHdr) + (size_t)2 * std::max<int64_t>(x.total, 1) * x.ldb * sizeof(double);
+    x.region_bytes = sizeof(XHdr) + (size_t)2 * nranks * std::max<int64_t>(x.total, 1) * x.ldb * sizeof(double);
     IB_CUDA(cudaMalloc(&x.region, x.region_bytes));
     IB_CUDA(cudaMemset(x.region, 0, x.region_bytes));
     x.peer[rank] = x.region;
