@@ -107,7 +107,98 @@ public:
         ib_check(ib_w_apply_dev(h, dX, ldx, nvar, dY, ldy, force_conservation, stream));
     }
 };
+/** Several matrices applied to the SAME device-resident fields in one call (the coupler's EvI and AvI on ice_ovalsI,
+IceCoupler.cpp:445-446): two wide matrices are stacked and applied in one pass over X. */
+inline void apply_many_dev(std::vector<Weighted const *> const &mats, const double *dX, long ldx, int nvar, std::vector<double *> const &dY,
+                           std::vector<long> const &ldy, bool force_conservation = true, void *stream = nullptr)
+{
+    std::vector<const ib_weighted *> h;
+    std::vector<int64_t> ld(ldy.begin(), ldy.end());
+    for (auto m : mats) h.push_back(m->handle());
+    ib_check(ib_w_apply_many_dev((int32_t)mats.size(), h.data(), dX, ldx, nvar, dY.data(), ld.data(), force_conservation, stream));
+}
 }   // namespace linear
+
+/** Merge of the sheets' A- / E-grid contributions across GPUs (one rank = one process = one GPU = one sheet) over NVLink
+peer memory: the device-resident replacement of "gather to the GCM root + VectorMultivec::to_dense" (modele/
+GCMCoupler_ModelE.cpp:761-793, multivec.cpp:35-81).  The host supplies the one piece of communication it already has (MPI
+in the reference): `allgather(send, bytes, recv)` must fill recv with every rank's `bytes` bytes in rank order.
+
+    SheetExchange x(rank, nranks, nvar_max, allgather);
+    x.add_part(gcm.nE(), *EvI_unscaled);  x.add_part(gcm.nA(), *AvI_unscaled);      // dims[0] + wM of this rank's matrices
+    x.connect();
+    ... every coupling step:  x.merge({dYE, dYA}, {ldE, ldA}, nvar, stream);        // unscaled sums in, merged values out
+*/
+class SheetExchange {
+public:
+    typedef std::function<void(const void *send, size_t bytes, void *recv)> AllGather;
+private:
+    ib_xchg *h = nullptr;
+    int rank, nranks, nvar_max;
+    AllGather allgather;
+    struct Part { int64_t n_sparse; std::vector<int64_t> ids; std::vector<double> w; bool scaled; };
+    std::vector<Part> parts;
+public:
+    SheetExchange(int _rank, int _nranks, int _nvar_max, AllGather const &ag) : rank(_rank), nranks(_nranks), nvar_max(_nvar_max), allgather(ag) {}
+    SheetExchange(SheetExchange const &) = delete;
+    ~SheetExchange() { if (h) ib_xchg_free(h); }
+    /** scaled = false: the matrix is unscaled (the coupler's E1vI_unscaled) and the merge divides every row by its weight;
+        scaled = true: rows are already divided by their own weight, only the shared cells are rewritten */
+    void add_part(long n_sparse, linear::Weighted const &M, bool scaled = false) { parts.push_back(Part{n_sparse, M.dim(0), M.get_weights(0), scaled}); }
+    void connect()
+    {
+        const int np = (int)parts.size();
+        std::vector<int64_t> nshared((size_t)np);
+        struct Plan { std::vector<int32_t> loc; std::vector<uint64_t> owners; std::vector<double> wtot; };
+        std::vector<Plan> plans((size_t)np);
+        for (int p = 0; p < np; ++p) {
+            // gather every rank's ids and weights of this grid: counts first, then padded payloads
+            int64_t mine = (int64_t)parts[p].ids.size();
+            std::vector<int64_t> cnt((size_t)nranks);
+            allgather(&mine, sizeof mine, cnt.data());
+            int64_t mx = 0;
+            for (auto c : cnt) mx = c > mx ? c : mx;
+            std::vector<int64_t> sid((size_t)mx, -1), rid((size_t)mx * nranks);
+            std::vector<double> sw((size_t)mx, 0.0), rw((size_t)mx * nranks);
+            std::copy(parts[p].ids.begin(), parts[p].ids.end(), sid.begin());
+            std::copy(parts[p].w.begin(), parts[p].w.end(), sw.begin());
+            allgather(sid.data(), sizeof(int64_t) * (size_t)mx, rid.data());
+            allgather(sw.data(), sizeof(double) * (size_t)mx, rw.data());
+            std::vector<const int64_t *> ptr((size_t)nranks);
+            for (int r = 0; r < nranks; ++r) ptr[r] = rid.data() + (size_t)r * mx;
+            int64_t ns = ib_xchg_plan(nranks, ptr.data(), cnt.data(), parts[p].n_sparse, rank, nullptr, nullptr, nullptr);
+            ib_check(ns);
+            std::vector<int64_t> shared((size_t)ns);
+            Plan &P = plans[p];
+            P.loc.resize((size_t)ns); P.owners.resize((size_t)ns); P.wtot.assign((size_t)ns, 0.0);
+            if (ns) ib_check(ib_xchg_plan(nranks, ptr.data(), cnt.data(), parts[p].n_sparse, rank, shared.data(), P.loc.data(), P.owners.data()));
+            // summed weights of the shared cells over their owners, added in rank order
+            std::map<int64_t, int64_t> where;
+            for (int64_t k = 0; k < ns; ++k) where[shared[k]] = k;
+            for (int r = 0; r < nranks; ++r)
+                for (int64_t i = 0; i < cnt[r]; ++i) {
+                    auto it = where.find(ptr[r][i]);
+                    if (it != where.end()) P.wtot[(size_t)it->second] += rw[(size_t)r * mx + i];
+                }
+            nshared[p] = ns;
+        }
+        ib_check(ib_xchg_create(&h, rank, nranks, np, nshared.data(), nvar_max));
+        const size_t hb = (size_t)ib_xchg_handle_bytes();
+        std::vector<char> mine(hb), all(hb * nranks);
+        ib_check(ib_xchg_get_handle(h, mine.data()));
+        allgather(mine.data(), hb, all.data());
+        ib_check(ib_xchg_open(h, all.data()));
+        for (int p = 0; p < np; ++p)
+            ib_check(ib_xchg_set_part(h, p, (int64_t)parts[p].ids.size(), plans[p].loc.data(), plans[p].owners.data(), plans[p].wtot.data(),
+                                      parts[p].w.data(), parts[p].scaled));
+    }
+    void merge(std::vector<double *> const &dY, std::vector<long> const &ldy, int nvar, void *stream = nullptr)
+    {
+        std::vector<int64_t> ld(ldy.begin(), ldy.end());
+        ib_check(ib_xchg_merge_dev(h, dY.data(), ld.data(), nvar, stream));
+    }
+    void status() { ib_check(ib_xchg_status(h)); }
+};
 
 class GCMRegridder_Standard;
 

@@ -56,6 +56,32 @@ int main(int argc, char **argv)
     CHECK(EvI->conservative() && EvI->scaled());
     CHECK(EvI->dim(1) == IvE->dim(0) && EvI->dim(0) == IvE->dim(1));
 
+    // EvI and AvI on the same device-resident fields in one call (IceCoupler.cpp:445-446), then the single-rank form of the
+    // multi-GPU merge: with one rank no cell is shared, so unscaled sums / wM must equal the scaled matrices' results
+    {
+        auto rmu = gcm.regrid_matrices(0, em, RegridParams(false, true));
+        auto EvIu = rmu->matrix("EvI");
+        auto AvIu = rmu->matrix("AvI");
+        const int nv = 64;
+        const long nc = EvI->shape()[1], nE2 = EvI->shape()[0], nA2 = AvI->shape()[0];
+        std::vector<double> X((size_t)nc * nv);
+        for (size_t k = 0; k < X.size(); ++k) X[k] = 0.25 + 0.001 * (double)(k % 977);
+        detail::DevBuf dX(X.size()), dE((size_t)nE2 * nv), dA((size_t)nA2 * nv), dE2((size_t)nE2 * nv), dA2((size_t)nA2 * nv);
+        ib_check(ib_dev_upload(dX.p, X.data(), (int64_t)(X.size() * sizeof(double))));
+        linear::apply_many_dev({EvI.get(), AvI.get()}, dX.d(), nv, nv, {dE.d(), dA.d()}, {nv, nv});
+        linear::apply_many_dev({EvIu.get(), AvIu.get()}, dX.d(), nv, nv, {dE2.d(), dA2.d()}, {nv, nv});
+        SheetExchange xch(0, 1, nv, [](const void *send, size_t bytes, void *recv) { std::memcpy(recv, send, bytes); });
+        xch.add_part(gcm.nE(), *EvIu);
+        xch.add_part(gcm.nA(), *AvIu);
+        xch.connect();
+        xch.merge({dE2.d(), dA2.d()}, {nv, nv}, nv);
+        xch.status();
+        std::vector<double> a((size_t)nE2 * nv), b((size_t)nE2 * nv);
+        ib_check(ib_dev_download(a.data(), dE.p, (int64_t)(a.size() * sizeof(double))));
+        ib_check(ib_dev_download(b.data(), dE2.p, (int64_t)(b.size() * sizeof(double))));
+        for (size_t k = 0; k < a.size(); ++k) CHECK(std::fabs(a[k] - b[k]) <= 1e-12 * std::fabs(a[k]));
+    }
+
     // conservation: sum wM * (EvI f) == sum Mw * f
     long nId = EvI->shape()[1], nEd = EvI->shape()[0];
     std::vector<double> f((size_t)nId);
