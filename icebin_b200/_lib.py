@@ -54,6 +54,9 @@ SIGNATURES = {
     "ib_rm_matrix_d": (C.c_int, [vp, cp, vp, vp, C.c_int, C.c_int, vp, PP]),
     "ib_w_free": (None, [vp]),
     "ib_w_create_csr": (C.c_int, [PP, i64, i64, vp, vp, vp, vp, vp, C.c_int]),
+    "ib_w_aggregate": (C.c_int, [vp, C.c_int, vp, vp, i64, vp, PP]),
+    "ib_w_set_weights": (C.c_int, [vp, vp, vp, C.c_int, C.c_int]),
+    "ib_w_set_dim": (C.c_int, [vp, C.c_int, i64, i64, vp]),
     "ib_w_info": (C.c_int, [vp, vp]),
     "ib_w_get_csr": (C.c_int, [vp, vp, vp, vp]),
     "ib_w_get_coo": (C.c_int, [vp, vp, vp, vp]),

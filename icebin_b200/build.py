@@ -27,6 +27,7 @@ UNITS = {
     "hntr.cu": [],
     "merge.cu": ["-fmad=false"],
     "xchg.cu": [],
+    "modele.cu": ["-fmad=false"],
     "capi.cu": [],
 }
 

@@ -94,6 +94,9 @@ void combine_chunks(int, Weighted *const *, bool, int64_t *, int64_t *, double *
 int64_t exgrid_rectilinear(int, const int32_t *, const double *, const int64_t *, int, const double *, int, const double *, int, int32_t *,
                            double *, cudaStream_t);
 
+// modele.cu
+std::unique_ptr<Weighted> aggregate(Weighted &, int, const int32_t *, const double *, int64_t, const double *, cudaStream_t);
+
 // merge.cu
 void multivec_to_dense(int64_t, const int64_t *, const double *, const double *, int, int64_t, double, double *, double *, cudaStream_t);
 void merge_pack(const double *, int64_t, int, const int32_t *, int64_t, double *, cudaStream_t);
@@ -496,6 +499,58 @@ int ib_w_create_csr(ib_weighted **out, int64_t nrow, int64_t ncol, const int32_t
     if (Mw) w.Mw.upload(Mw, (size_t)ncol); else w.Mw.zero();
     IB_CUDA(cudaStreamSynchronize(s));
     *out = W.release();
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_w_aggregate(const ib_weighted *W, int side, const int32_t *map, const double *factor, int64_t n_new, const double *other_scale,
+                   ib_weighted **out)
+{
+    IB_TRY
+    if (!W || !out || (side != 0 && side != 1) || n_new < 0 || (!map && (side == 0 ? W->w->nrow : W->w->ncol) > 0))
+        fail(IB_ERR_ARG, "ib_w_aggregate: bad argument");
+    Weighted &w = *W->w;
+    const int64_t n_old = side == 0 ? w.nrow : w.ncol;
+    for (int64_t i = 0; i < n_old; ++i)
+        if (map[i] >= n_new) fail(IB_ERR_ARG, "ib_w_aggregate: map[%ld] = %d outside the new extent %ld", (long)i, map[i], (long)n_new);
+    std::unique_ptr<ib_weighted> N(new ib_weighted);
+    N->w = aggregate(w, side, map, factor, n_new, other_scale, w.stream);
+    *out = N.release();
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_w_set_weights(ib_weighted *W, const double *wM, const double *Mw, int conservative, int scaled)
+{
+    IB_TRY
+    if (!W) fail(IB_ERR_ARG, "ib_w_set_weights: bad argument");
+    Weighted &w = *W->w;
+    if (wM) w.wM.upload(wM, (size_t)w.nrow);
+    if (Mw) w.Mw.upload(Mw, (size_t)w.ncol);
+    w.conservative = conservative != 0;
+    w.scaled = scaled != 0;
+    w.cons_v.release();
+    IB_CUDA(cudaStreamSynchronize(w.stream));
+    return IB_OK;
+    IB_CATCH
+}
+
+int ib_w_set_dim(ib_weighted *W, int which, int64_t sparse_extent, int64_t n, const int64_t *ids)
+{
+    IB_TRY
+    if (!W || which < 0 || which > 1 || n < 0 || (n && !ids)) fail(IB_ERR_ARG, "ib_w_set_dim: bad argument");
+    Weighted &w = *W->w;
+    if (n != (which ? w.ncol : w.nrow)) fail(IB_ERR_DIM, "ib_w_set_dim: %ld ids for a dimension of dense extent %ld", (long)n, (long)(which ? w.ncol : w.nrow));
+    for (int64_t i = 0; i < n; ++i)
+        if (ids[i] < 0 || ids[i] >= sparse_extent) fail(IB_ERR_ARG, "ib_w_set_dim: id %ld outside the sparse extent %ld", (long)ids[i], (long)sparse_extent);
+    std::unique_ptr<Dim> d(new Dim);
+    d->pending.assign(ids, ids + n);
+    d->dense_extent = n;
+    d->set_sparse_extent(sparse_extent, w.stream);
+    if (n == 0) d->sparse_extent = sparse_extent;
+    IB_CUDA(cudaStreamSynchronize(w.stream));
+    w.owned[which] = std::move(d);
+    w.dims[which] = w.owned[which].get();
     return IB_OK;
     IB_CATCH
 }

@@ -89,11 +89,14 @@ def _pieces_1d(n, d, a, off):
 
 
 def make_gcm_and_sheet(shape="greenland_5km", anchor=(40, 60), im=144, jm=90, name=None, margin=1,
-                       gridA=None):
+                       gridA=None, cell=None):
     """Build (GridA, SheetGrid).  `anchor` = (i, j) of the A cell holding the ice grid's lower-left corner region.
-    Pass an existing `gridA` to add a further sheet to the same GCM grid (its realised set must cover the sheet)."""
+    Pass an existing `gridA` to add a further sheet to the same GCM grid (its realised set must cover the sheet).
+    cell = (width, height) of a GCM cell in the ice-grid plane (default: the 2.5 x 2 degree cell; the ModelE ocean grid of
+    GCMRegridder_ModelE is the same grid refined 2:1, cell = (A_W / 2, A_H / 2))."""
     nx, ny, dxkm = SHEET_SHAPES[shape] if isinstance(shape, str) else shape
     dx = dxkm * KM
+    A_W, A_H = cell if cell is not None else (globals()["A_W"], globals()["A_H"])
     px, lx = _pieces_1d(nx, dx, A_W, A_OFF[0])
     py, ly = _pieces_1d(ny, dx, A_H, A_OFF[1])
     np_, nq = int(px.max()) + 1, int(py.max()) + 1

@@ -130,6 +130,17 @@ void ib_w_free(ib_weighted *);
 int ib_w_create_csr(ib_weighted **out, int64_t nrow, int64_t ncol, const int32_t *rowptr, const int32_t *col,
                     const double *val, const double *wM, const double *Mw, int conservative);
 
+/* The device step of GCMRegridder_ModelE's mismatched regridding (modele/GCMRegridder_ModelE.cpp:285-307 crop_mvp, :367-386,
+ * :418-432; icebin_b200/modele.py holds the small GCM-side factors): re-index one side of a matrix -- side 0: row r becomes
+ * map[r], side 1: column c becomes map[c]; map < 0 drops the entry -- scale every entry by factor[old index] (NULL: 1) and by
+ * other_scale[index on the other side] (NULL: 1; applied first, as the reference scales the large matrix before the product),
+ * and add up the entries that now coincide, in storage order.  n_new: dense extent of the re-indexed side.  The result
+ * has identity dims and zero weights: ib_w_set_dim / ib_w_set_weights complete it. */
+int ib_w_aggregate(const ib_weighted *, int side, const int32_t *map, const double *factor, int64_t n_new, const double *other_scale,
+                   ib_weighted **out);
+int ib_w_set_weights(ib_weighted *, const double *wM, const double *Mw, int conservative, int scaled);   /* NULL: keep */
+int ib_w_set_dim(ib_weighted *, int which, int64_t sparse_extent, int64_t n, const int64_t *ids);        /* dense -> sparse ids */
+
 /* info[0..7] = nrow, ncol, nnz, conservative, scaled, sparse_extent(dim0), sparse_extent(dim1), reserved */
 int ib_w_info(const ib_weighted *, int64_t *info);
 /* matrix in CSR (rows = output space, columns ascending inside a row) and as sorted COO (to_coo()) */

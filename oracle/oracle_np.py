@@ -237,3 +237,122 @@ class Hntr:
             for jb in {0, jmB - 1}:
                 B[jb, :] = self.datmis if np.any(B[jb] == self.datmis) else B[jb].sum() / imB
         return B.ravel()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GCMRegridder_ModelE (slib/icebin/modele/GCMRegridder_ModelE.cpp:130-435, topo.cpp:46-240): a literal restatement with
+# scipy sparse products, on top of the C++ oracle's ocean-grid matrices.  TEST INFRASTRUCTURE.  Parity unpinned: the
+# reference holds no test or golden vector for these matrices.
+class ModelE:
+    """go: oracle Gcm over the OCEAN grid; specO / specA: (im, jm, offi, dlat) of the ocean / atmosphere Hntr grids."""
+
+    def __init__(self, go, sheet, elevmaskI, foceanAOp, foceanAOm, specO, eq_rad, nhc, nG):
+        from oracle import orc
+        self.go, self.sheet, self.em = go, sheet, elevmaskI
+        self.fp, self.fm = np.asarray(foceanAOp, float), np.asarray(foceanAOm, float)
+        self.nO = specO[0] * specO[1]
+        self.specA = (specO[0] // 2, specO[1] // 2, specO[2] * 0.5, specO[3] * 2.0)       # make_hntrA, hntr.cpp:232-241
+        self.nA = self.specA[0] * self.specA[1]
+        self.nhc, self.nG = nhc, nG
+        self.ov = orc.Hntr(specO, self.specA).matrix(eq_rad)          # Hntr(B = O, A = A).overlap: (iO, iA, area)
+
+    @staticmethod
+    def _sset(ids=()):
+        d = {}
+        for s in ids:
+            d.setdefault(int(s), len(d))
+        return d
+
+    def helper(self, X, G, dimIp=None):
+        import scipy.sparse as sp
+        m = lambda spec, scale, correctA, dims: self.go.matrix(self.sheet, self.em, spec, scale=scale, correctA=correctA, dims=dims)
+        AOpvGp_c = m("Av" + G, False, True, (None, dimIp))                                 # :185-188
+        wAOp, dimAOp, dimIp = AOpvGp_c.wM, self._sset(AOpvGp_c.dims[0]), AOpvGp_c.dims[1]
+        # compute_wAOm (topo.cpp:84-110)
+        dimAOm = self._sset(s for s in dimAOp if self.fm[s] == 0)
+        sc = sp.lil_matrix((len(dimAOm), len(dimAOp)))
+        for s, dp in dimAOp.items():                                                       # scaled_AOmvAOp (topo.cpp:46-80)
+            fcont_p, fcont_m = 1.0 - self.fp[s], 1.0 - self.fm[s]
+            if fcont_m == 0.0:
+                continue
+            assert fcont_m == 1.0
+            if fcont_p == 0.0:
+                continue
+            sc[dimAOm[s], dp] = 1.0 / fcont_p
+        wAOm = sc.tocsr() @ wAOp
+        if X == "A":
+            XOpvGp = m("Av" + G, False, False, (AOpvGp_c.dims[0], dimIp))                  # :252-259
+            dimXOp, dimXOm, wXOm = dimAOp, dimAOm, wAOm
+            dimXAm = {}
+            r, c, v = [], [], []
+            for io, ia, a in zip(*self.ov):                                                # :264-273, transposed
+                if int(io) in dimAOm:
+                    r.append(dimXAm.setdefault(int(ia), len(dimXAm))); c.append(dimAOm[int(io)]); v.append(a)
+        else:
+            XOpvGp = m("Ev" + G, False, False, (None, dimIp))                              # :208-213
+            dimXOp = self._sset(XOpvGp.dims[0])
+            EOpvAOp = m("EvA", False, False, (None, None))                                 # :219-221
+            dimXOm = {}
+            er, ec, ev = [], [], []
+            for rr, cc, vv in zip(EOpvAOp.row, EOpvAOp.col, EOpvAOp.val):                  # column-major order (topo.cpp:211-240)
+                sA = int(EOpvAOp.dims[1][cc])
+                if sA in dimAOm:
+                    er.append(dimXOm.setdefault(int(EOpvAOp.dims[0][rr]), len(dimXOm))); ec.append(dimAOm[sA]); ev.append(vv)
+            EOmvAOm = sp.csr_matrix((ev, (er, ec)), shape=(len(dimXOm), len(dimAOm)))
+            with np.errstate(divide="ignore"):
+                EOmvAOms = 1.0 / np.asarray(EOmvAOm.sum(0)).ravel()                        # sum(EOmvAOm, 1, '-')
+            wXOm = EOmvAOm @ sp.diags(EOmvAOms) @ wAOm                                     # :226-229
+            dimXAm = {}
+            r, c, v = [], [], []
+            for io, ia, a in zip(*self.ov):                                                # raw_EOvEA (topo.cpp:112-208), transposed
+                if int(io) not in dimAOm:
+                    continue
+                for ihc in range(self.nhc):
+                    sEO = ihc * self.nO + int(io)
+                    if sEO not in dimXOm or wXOm[dimXOm[sEO]] == 0:
+                        continue
+                    r.append(dimXAm.setdefault(ihc * self.nA + int(ia), len(dimXAm))); c.append(dimXOm[sEO]); v.append(wXOm[dimXOm[sEO]])
+        XAmvXOm = sp.csr_matrix((v, (r, c)), shape=(len(dimXAm), len(dimXOm)))
+        with np.errstate(divide="ignore"):
+            XAmvXOms = 1.0 / np.asarray(XAmvXOm.sum(0)).ravel()                            # :277
+        wXAm = XAmvXOm @ sp.diags(XAmvXOms) @ wXOm                                         # :281-282
+        return dict(XOpvGp=XOpvGp, dimXOp=dimXOp, dimXOm=dimXOm, dimXAm=dimXAm, dimIp=dimIp, XAmvXOm=XAmvXOm, XAmvXOms=XAmvXOms,
+                    wXAm=wXAm)
+
+    @staticmethod
+    def crop_mvp(dimAm, dimAp_ids, index, M):
+        """crop_mvp (:285-307): re-index dimension `index` of M from dense Ap to dense Am, dropping what is not in dimAm."""
+        import scipy.sparse as sp
+        M = M.tocoo()
+        idx = [M.row, M.col]
+        new = np.array([dimAm.get(int(dimAp_ids[i]), -1) for i in idx[index]], dtype=np.int64)
+        keep = new >= 0
+        idx[index] = new
+        shape = list(M.shape)
+        shape[index] = len(dimAm)
+        return sp.csr_matrix((M.data[keep], (idx[0][keep], idx[1][keep])), shape=shape)
+
+    def XAmvGp(self, X, G, scale=True):
+        """compute_XAmvGp (:318-386) -> (dims[0] ids, dims[1] ids, M csr, wM, Mw)"""
+        import scipy.sparse as sp
+        H = self.helper(X, G)
+        W = H["XOpvGp"]
+        Mo = sp.csr_matrix((W.val, (W.row, W.col)), shape=W.shape)
+        with np.errstate(divide="ignore"):
+            sXOpvGp = 1.0 / W.wM
+            sXAm = 1.0 / np.asarray(H["XAmvXOm"].sum(1)).ravel()
+        rowscale = sXAm if scale else H["wXAm"] * sXAm
+        M = sp.diags(rowscale) @ H["XAmvXOm"] @ self.crop_mvp(H["dimXOm"], W.dims[0], 0, sp.diags(sXOpvGp) @ Mo)
+        return np.array(list(H["dimXAm"]), np.int64), np.asarray(H["dimIp"]), M.tocsr(), H["wXAm"], W.Mw
+
+    def GpvXAm(self, G, X, scale=True):
+        """compute_GpvXAm (:388-435)"""
+        import scipy.sparse as sp
+        H = self.helper(X, G)
+        W = self.go.matrix(self.sheet, self.em, G + "v" + X, scale=False, correctA=False, dims=(H["dimIp"], H["XOpvGp"].dims[0]))
+        Mo = sp.csr_matrix((W.val, (W.row, W.col)), shape=W.shape)
+        if scale:
+            with np.errstate(divide="ignore"):
+                Mo = sp.diags(1.0 / W.wM) @ Mo
+        M = self.crop_mvp(H["dimXOm"], W.dims[1], 1, Mo) @ sp.diags(H["XAmvXOms"]) @ H["XAmvXOm"].T
+        return np.asarray(W.dims[0]), np.array(list(H["dimXAm"]), np.int64), M.tocsr(), H["XOpvGp"].Mw, H["wXAm"]
