@@ -342,8 +342,11 @@ class ModelE:
             sXOpvGp = 1.0 / W.wM
             sXAm = 1.0 / np.asarray(H["XAmvXOm"].sum(1)).ravel()
         rowscale = sXAm if scale else H["wXAm"] * sXAm
-        M = sp.diags(rowscale) @ H["XAmvXOm"] @ self.crop_mvp(H["dimXOm"], W.dims[0], 0, sp.diags(sXOpvGp) @ Mo)
-        return np.array(list(H["dimXAm"]), np.int64), np.asarray(H["dimIp"]), M.tocsr(), H["wXAm"], W.Mw
+        M = (H["XAmvXOm"] @ self.crop_mvp(H["dimXOm"], W.dims[0], 0, sp.diags(sXOpvGp) @ Mo)).tocsr()
+        # Eigen's diagonal * sparse keeps the pattern where the scale is 0 (unscaled rows with wXAm == 0: continent for ModelE,
+        # ocean for the ice model); scipy's diags() product would drop those entries, so scale the stored values in place
+        M.data *= np.repeat(rowscale, np.diff(M.indptr))
+        return np.array(list(H["dimXAm"]), np.int64), np.asarray(H["dimIp"]), M, H["wXAm"], W.Mw
 
     def GpvXAm(self, G, X, scale=True):
         """compute_GpvXAm (:388-435)"""
