@@ -712,34 +712,42 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const int4 *__restrict_
 }
 
 // ---- conservation correction (ibmisc Weighted_Eigen::apply_e; matrix_formats.rst:156-165) ---------------
-// out[b][f] = sum over rows r of block b's slice of w[r] * A[r][f]
-__global__ void __launch_bounds__(256) wdot_partial_kernel(const double *__restrict__ w, const double *__restrict__ A, int64_t lda,
-                                                           int64_t nrow, int nvar, int64_t rows_per_block, double *__restrict__ out)
+// The whole correction of the input in ONE launch: a block owns 8 fields and walks ALL rows twice.  Pass 1: thread
+// (rg, fi) adds up rows rg, rg + 64, ... of field fi for both weight vectors (independent 64-byte-coalesced loads, all in
+// flight at once at 1120 rows); the 64 row groups are added in order through shared memory (deterministic):
+// factor[f] = (wa . A)[f] / (wb . A)[f].  Pass 2: As[r][f] = A[r][f] * factor[f] (the rows are still in L1 / L2).
+__global__ void __launch_bounds__(512) cons_scale_kernel(const double *__restrict__ wa, const double *__restrict__ wb,
+                                                         const double *__restrict__ A, int64_t lda, int64_t nrow, int nvar,
+                                                         double *__restrict__ As, int64_t ldas)
 {
-    int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(nrow, r0 + rows_per_block);
-    for (int f = threadIdx.x; f < nvar; f += blockDim.x) {
-        double s = 0;
-        for (int64_t r = r0; r < r1; ++r) s = s + w[r] * A[r * lda + f];
-        out[(int64_t)blockIdx.x * nvar + f] = s;
+    __shared__ double sa_s[64][8], sb_s[64][8];
+    __shared__ double fac_s[8];
+    const int rg = threadIdx.x >> 3, fi = threadIdx.x & 7;
+    const int f = blockIdx.x * 8 + fi;
+    double sa = 0, sb = 0;
+    if (f < nvar) {
+#pragma unroll 4
+        for (int64_t r = rg; r < nrow; r += 64) {
+            const double x = A[r * lda + f];
+            sa = sa + __ldg(wa + r) * x;
+            sb = sb + __ldg(wb + r) * x;
+        }
     }
-}
-__global__ void wdot_final_kernel(const double *__restrict__ pa, int nba, const double *__restrict__ pb, int nbb, int nvar,
-                                  double *__restrict__ factor)
-{
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nvar) return;
-    double ta = 0, tb = 0;
-    for (int b = 0; b < nba; ++b) ta = ta + pa[(int64_t)b * nvar + f];
-    for (int b = 0; b < nbb; ++b) tb = tb + pb[(int64_t)b * nvar + f];
-    factor[f] = ta * (1. / tb);
-}
-__global__ void scale_copy_kernel(const double *__restrict__ X, int64_t ldx, double *__restrict__ Xs, int64_t ldxs, int64_t nrow, int nvar,
-                                  const double *__restrict__ factor)
-{
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t r = t / nvar;
-    int f = (int)(t - r * nvar);
-    if (r < nrow) Xs[r * ldxs + f] = X[r * ldx + f] * factor[f];
+    sa_s[rg][fi] = sa;
+    sb_s[rg][fi] = sb;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double ta = 0, tb = 0;
+#pragma unroll
+        for (int g = 0; g < 64; ++g) { ta = ta + sa_s[g][fi]; tb = tb + sb_s[g][fi]; }
+        fac_s[fi] = ta * (1. / tb);
+    }
+    __syncthreads();
+    if (f < nvar) {
+        const double fc = fac_s[fi];
+#pragma unroll 4
+        for (int64_t r = rg; r < nrow; r += 64) As[r * ldas + f] = A[r * lda + f] * fc;
+    }
 }
 // v[c] = sum_r M[r,c] * wM[r], columns walked in CSC order (rows ascending): deterministic
 __global__ void cons_v_kernel(const int32_t *colptr, const uint32_t *perm, const int32_t *row, const double *val, const double *wM,
@@ -773,16 +781,6 @@ static void compute_cons_v(Weighted &W, cudaStream_t s)
     seg_ptr_kernel<<<(unsigned)cdiv(nnz, 256), 256, 0, s>>>(csorted.p, nnz, ncol, colptr.p);
     IB_LAUNCHED();
     cons_v_kernel<<<(unsigned)cdiv(ncol, 128), 128, 0, s>>>(colptr.p, w1 ? p1.p : p0.p, row.p, W.val.p, W.wM.p, ncol, W.cons_v.p);
-    IB_LAUNCHED();
-}
-
-static void wdot(const double *w, const double *A, int64_t lda, int64_t nrow, int nvar, DBuf<double> &part, int &nb, cudaStream_t s)
-{
-    nb = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(nrow, 16)), 4 * sm_count());     // short row runs: many blocks, little latency each
-    int64_t rpb = cdiv(std::max<int64_t>(nrow, 1), nb);
-    nb = (int)cdiv(std::max<int64_t>(nrow, 1), rpb);
-    part.alloc((size_t)nb * nvar, s);
-    wdot_partial_kernel<<<nb, 256, 0, s>>>(w, A, lda, nrow, nvar, rpb, part.p);
     IB_LAUNCHED();
 }
 
@@ -850,24 +848,17 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
     //   B = B0 * (Mw.A)/(wM.B0)  with  wM.(M A) = (M^T wM).A =: v.A ,
     // so both dot products run over the (small) input fields, the factor is folded into a scaled copy of A, and the
     // large output is written once instead of being re-read twice.
+    if (ldx < nvar || ldy < nvar) fail(IB_ERR_ARG, "apply: leading dimension smaller than nvar");
     DBuf<double> Xscaled;
     if (!W.conservative && force_conservation) {
         compute_cons_v(W, s);
-        DBuf<double> pa, pb, factor((size_t)nvar, s);
-        int nba, nbb;
-        wdot(W.Mw.p, dX, ldx, W.ncol, nvar, pa, nba, s);
-        wdot(W.cons_v.p, dX, ldx, W.ncol, nvar, pb, nbb, s);
-        wdot_final_kernel<<<(unsigned)cdiv(nvar, 128), 128, 0, s>>>(pa.p, nba, pb.p, nbb, nvar, factor.p);
-        IB_LAUNCHED();
         const int64_t ldxs = (nvar + 1) & ~1;
         Xscaled.alloc((size_t)W.ncol * ldxs, s);
-        const int64_t tot = W.ncol * (int64_t)nvar;
-        scale_copy_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, s>>>(dX, ldx, Xscaled.p, ldxs, W.ncol, nvar, factor.p);
+        cons_scale_kernel<<<(unsigned)cdiv(nvar, 8), 512, 0, s>>>(W.Mw.p, W.cons_v.p, dX, ldx, W.ncol, nvar, Xscaled.p, ldxs);
         IB_LAUNCHED();
         dX = Xscaled.p;
         ldx = ldxs;
     }
-    if (ldx < nvar || ldy < nvar) fail(IB_ERR_ARG, "apply: leading dimension smaller than nvar");
     // wide matrices with about two nonzeros per column (EvI): one pass over X, no second kernel (apply_stream.cu)
     if (!row_api && g_tune.use_stream && apply_stream(W, nullptr, dX, ldx, nvar, dY, ldy, nullptr, 0, s)) return;
     make_plan(W, s);

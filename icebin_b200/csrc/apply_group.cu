@@ -1,27 +1,30 @@
 // apply_group.cu -- Y = M X for TALL matrices whose neighbouring rows name mostly the same columns: the sigma-smoothed
-// IvE / IvA (RegridMatrices_Dynamic.cpp:236-248, smoother.cpp:43-99): ~16 nonzeros per row, and the ~26 distinct columns
-// of 16 consecutive ice cells are the elevation classes their common neighbourhood feeds.
+// IvE / IvA (RegridMatrices_Dynamic.cpp:236-248, smoother.cpp:43-99): ~16 nonzeros per row, and the ~36 distinct columns
+// of 32 consecutive ice cells are the elevation classes their common neighbourhood feeds.
 //
 // Why not the other kernels.  X is small (E or A cells: L2-resident), Y is large (ice cells).  A kernel that reads one X
-// row per nonzero moves 16x the output through L2 (the chip's L2 delivers ~12 TB/s: 4.5 GB -> 0.4 ms, what
-// spmm_xs_kernel measured); keeping X rows in shared memory still costs one 16-byte shared-memory read per nonzero and
-// field pair (36 TB/s of LDS bandwidth: 125 us).  So the X values have to be reused from REGISTERS:
-//   item  = 16 consecutive rows; its distinct columns, ascending, cut into chunks of <= 8 columns;
-//   chunk = the X rows of its columns (ONE 1-D bulk async copy each: 4 KB at 512 fields) + a dense 8 x 16 coefficient
-//           table with a 16-bit presence mask per column, prepared once per matrix; a chunk is one stage of a
-//           shared-memory ring fed by a producer warp;
-//   a consumer warp owns a 64-field strip of the item: 16 running sums of one double2 per lane; for every column ONE
-//   shared-memory read of x serves the (up to) 16 rows that name it.  Rows that do not name a column carry a zero in the
-//   table, which adds nothing while x is finite; where a lane holds a NaN / Inf the presence bits take over, so a NaN in
-//   X reaches only the rows that name its cell (structural zeros are never multiplied into a sum).
-// Each row's terms are added in ascending column order, with fused multiply-add: fp64 FMA rate is what bounds this
-// kernel next to L2 (1.1 M nonzeros x 512 fields = 0.56 G multiply-adds; B200 measured 18.5 T DFMA/s, half of that for
-// separate DMUL + DADD), so results agree with the oracle to rounding (1e-12 gate), not bit for bit.
-// (First version: every warp its own pipeline with 512-byte copies -- 0.9 M copies per apply, one per ~60 ns and SM: the
-// copy engine, not L2 or the fp64 pipe, set the pace at 380 us.)
+// row per nonzero moves 16x the output through L2 (0.4 ms, what spmm_xs_kernel measured); keeping X rows in shared memory
+// and multiplying with DFMA still costs one shared-memory read per column and 36 LDS.128 per 128 DFMA -- measured 182 us
+// with the fp64 pipe 27 % busy, warps waiting on shared-memory loads (ncu: short scoreboard).  So the product is done as
+// small DENSE blocks on the fp64 tensor-core path (DMMA.8x8x4; B200 measured 72.5 G mma/s = 37 TFLOP/s, the same flops as
+// DFMA but 10 operand loads per 16 mma):
+//   item  = 32 consecutive rows = four m-tiles of 8 rows; its distinct columns, ordered by (first, last m-tile that names
+//           them) so that most 8-row x 4-column blocks of the item are either dense or empty, cut into chunks of 8 columns;
+//   chunk = the X rows of its columns (ONE 1-D bulk async copy each: 4 KB at 512 fields) + the coefficients of its
+//           2 k-steps x 4 m-tiles laid out in DMMA A-fragment order, a bit per non-empty block, and a 32-bit row-presence
+//           mask per column; prepared once per matrix; a chunk is one stage of a shared-memory ring fed by a producer warp;
+//   a consumer warp owns a 32-field strip of the item: 4 x 4 accumulator tiles; per k-step 4 B-fragment loads (X), one
+//   A-fragment load and 4 DMMA per non-empty block.  X rows sit 32 bytes apart modulo 128 in shared memory so that the
+//   B-fragment loads (4 rows x 8 fields) are conflict-free.
+// Rows that do not name a column of a non-empty block carry a zero coefficient, which adds nothing while x is finite;
+// where a warp sees a NaN / Inf in the k-step's X values the presence bits take over (scalar FMA path), so a NaN in X
+// reaches only the rows that name its cell (structural zeros are never multiplied into a sum).  The terms of a row are
+// added four columns at a time inside the tensor core, so results agree with the oracle to rounding (1e-12 gate), not bit
+// for bit.
 //
-// Roofline: HBM (Y written once: 12*nnz + 8*nvar*(nrow + ncol) algorithmic bytes); next bounds: L2 -> SM traffic of the
-// X rows (~1.6x the output at 5 km) and the fp64 pipe.
+// Roofline: HBM (Y written once: 12*nnz + 8*nvar*(nrow + ncol) algorithmic bytes); next bounds: the fp64 pipe (3.3 M
+// DMMA at 5 km: 45 us), the bulk-copy engine (one copy per ~60 ns and SM: 1.1 X rows per output row) and L2 -> SM
+// traffic.  (History: every warp its own pipeline with 512-byte copies 380 us -> CTA ring, 16-row items, DFMA 182 us.)
 #include <algorithm>
 #include <mutex>
 
@@ -31,80 +34,160 @@
 
 namespace ib {
 
-constexpr int GR_R = 16;                 // rows per item
-constexpr int GR_CH = 8;                 // columns per chunk
+constexpr int GR_R = 32;                 // rows per item (four 8-row m-tiles)
+constexpr int GR_CH = 8;                 // columns per chunk (two k-steps of 4)
 constexpr int GR_MAXD = 128;             // distinct columns per item the plan accepts
-// chunk record: ncols, pad[3] | cols[CH] | mask[CH] (uint16) + pad | coef[CH][16]
-constexpr int GR_OFF_COLS = 16, GR_OFF_MASK = GR_OFF_COLS + 4 * GR_CH, GR_OFF_COEF = GR_OFF_MASK + 2 * GR_CH + 16;
+// chunk record: ncols, block mask (bit 4*kstep + mtile), done mask (bit mtile), pad | cols[8] | rowmask[8] | coef[kstep 2][mtile 4][lane 32]
+constexpr int GR_OFF_COLS = 16, GR_OFF_RMASK = GR_OFF_COLS + 4 * GR_CH, GR_OFF_COEF = GR_OFF_RMASK + 4 * GR_CH;
 constexpr int GR_REC = GR_OFF_COEF + 8 * GR_CH * GR_R;
+constexpr int GR_SKEW = 32;              // bytes added to the shared-memory stride of an X row
 static_assert(GR_OFF_COEF % 16 == 0 && GR_REC % 16 == 0, "bulk copies move multiples of 16 bytes");
 
-// ---- plan: one thread per item, twice (count -> scan -> emit)
-__device__ int gr_distinct(const int32_t *rowptr, const int32_t *col, int64_t r0, int64_t r1, int32_t *list)
+// ---- plan: one warp per item, lane = row.  The rows' columns ascend (CSR), so the item's distinct columns come out of
+// a 32-way merge: the smallest head over the lanes is the next column, the lanes holding it are its rows.
+__device__ __forceinline__ int gr_next_column(const int32_t *col, int32_t &j, int32_t je, uint32_t &rows, bool &sorted)
 {
-    int n = 0;
-    for (int32_t j = rowptr[r0]; j < rowptr[r1]; ++j) {
-        const int32_t c = col[j];
-        int lo = 0, hi = n;                      // sorted insert
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (list[mid] < c) lo = mid + 1; else hi = mid; }
-        if (lo < n && list[lo] == c) continue;
-        if (n == GR_MAXD) return GR_MAXD + 1;
-        for (int k = n; k > lo; --k) list[k] = list[k - 1];
-        list[lo] = c;
-        ++n;
-    }
-    return n;
+    const int head = j < je ? col[j] : INT_MAX;
+    const int m = __reduce_min_sync(0xffffffffu, head);
+    rows = __ballot_sync(0xffffffffu, head == m);
+    if (head == m)
+        while (j < je && col[j] == m) ++j;                 // duplicate entries of a caller-supplied CSR
+    if (j < je && col[j] < m) sorted = false;
+    return m;
 }
-struct GrCountLoad {
-    const int32_t *rowptr, *col;
-    int64_t nrow;
-    int *too_wide;
-    __device__ uint32_t operator()(int64_t it) const
-    {
-        int32_t list[GR_MAXD];
-        const int64_t r0 = it * GR_R, r1 = min(nrow, r0 + GR_R);
-        const int n = gr_distinct(rowptr, col, r0, r1, list);
-        if (n > GR_MAXD) { atomicExch(too_wide, 1); return 1u; }
-        return (uint32_t)max(1, (n + GR_CH - 1) / GR_CH);
+
+__global__ void __launch_bounds__(128) gr_count_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t nrow,
+                                                       int64_t nitems, uint32_t *__restrict__ counts, int *__restrict__ refuse)
+{
+    const int64_t it = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (it >= nitems) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = it * GR_R + lane;
+    int32_t j = r < nrow ? rowptr[r] : 0;
+    const int32_t je = r < nrow ? rowptr[r + 1] : 0;
+    bool sorted = true;
+    int D = 0;
+    for (;; ++D) {
+        uint32_t rows;
+        if (gr_next_column(col, j, je, rows, sorted) == INT_MAX) break;
     }
+    if (!__all_sync(0xffffffffu, sorted) || D > GR_MAXD) { if (lane == 0) atomicExch(refuse, 1); D = 0; }
+    if (lane == 0) counts[it] = (uint32_t)max(1, (D + GR_CH - 1) / GR_CH);
+}
+
+struct GrCountLoad {
+    const uint32_t *counts;
+    __device__ uint32_t operator()(int64_t it) const { return counts[it]; }
 };
-struct GrEmit {
-    const int32_t *rowptr, *col;
-    const double *val;
-    int64_t nrow;
+struct GrItemEmit {
     int4 *items;
-    unsigned char *chunks;
+    int64_t nrow;
     __device__ void operator()(int64_t it, uint32_t prefix, uint32_t nch) const
     {
-        int32_t list[GR_MAXD];
-        const int64_t r0 = it * GR_R, r1 = min(nrow, r0 + GR_R);
-        const int n = gr_distinct(rowptr, col, r0, r1, list);
-        items[it] = make_int4((int)r0, (int)prefix, (int)(prefix + nch), (int)(r1 - r0));
-        for (uint32_t q = 0; q < nch; ++q) {
-            unsigned char *rec = chunks + (size_t)(prefix + q) * GR_REC;
-            const int c0 = (int)q * GR_CH, nc = max(0, min(GR_CH, n - c0));
-            reinterpret_cast<int32_t *>(rec)[0] = nc;
-            int32_t *cols = reinterpret_cast<int32_t *>(rec + GR_OFF_COLS);
-            uint16_t *mask = reinterpret_cast<uint16_t *>(rec + GR_OFF_MASK);
-            double *coef = reinterpret_cast<double *>(rec + GR_OFF_COEF);
-            for (int k = 0; k < GR_CH; ++k) { cols[k] = k < nc ? list[c0 + k] : 0; mask[k] = 0; }
-            for (int k = 0; k < GR_CH * GR_R; ++k) coef[k] = 0.0;
-        }
-        for (int64_t r = r0; r < r1; ++r)
-            for (int32_t j = rowptr[r]; j < rowptr[r + 1]; ++j) {
-                const int32_t c = col[j];
-                int lo = 0, hi = n;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (list[mid] < c) lo = mid + 1; else hi = mid; }
-                unsigned char *rec = chunks + (size_t)(prefix + lo / GR_CH) * GR_REC;
-                const int k = lo % GR_CH, rr = (int)(r - r0);
-                // duplicate (row, column) entries of a caller-supplied CSR add up, in storage order
-                double *cf = reinterpret_cast<double *>(rec + GR_OFF_COEF) + k * GR_R + rr;
-                uint16_t *mk = reinterpret_cast<uint16_t *>(rec + GR_OFF_MASK) + k;
-                *cf = (*mk >> rr & 1) ? *cf + val[j] : val[j];
-                *mk |= (uint16_t)(1u << rr);
-            }
+        const int64_t r0 = it * GR_R;
+        items[it] = make_int4((int)r0, (int)prefix, (int)(prefix + nch), (int)min((int64_t)GR_R, nrow - r0));
     }
 };
+
+__global__ void __launch_bounds__(128) gr_emit_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                      const double *__restrict__ val, int64_t nrow, int64_t nitems,
+                                                      const int4 *__restrict__ items, unsigned char *__restrict__ chunks)
+{
+    __shared__ int32_t s_cols[4][GR_MAXD];
+    __shared__ uint32_t s_rows[4][GR_MAXD];
+    __shared__ unsigned char s_pos[4][GR_MAXD];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t it = (int64_t)blockIdx.x * 4 + w;
+    if (it >= nitems) return;
+    const int64_t r = it * GR_R + lane;
+    const int32_t jb = r < nrow ? rowptr[r] : 0, je = r < nrow ? rowptr[r + 1] : 0;
+    int32_t j = jb;
+    bool sorted = true;
+    int D = 0;
+    for (;; ++D) {
+        uint32_t rows;
+        const int c = gr_next_column(col, j, je, rows, sorted);
+        if (c == INT_MAX) break;
+        if (lane == 0 && D < GR_MAXD) { s_cols[w][D] = c; s_rows[w][D] = rows; }
+    }
+    if (D > GR_MAXD) D = 0;                                  // refused by the count pass; keep the writes in bounds
+    __syncwarp();
+    // order the columns by (first, last) m-tile that names them, then by column: a stable counting sort over 16 keys
+    int key[GR_MAXD / 32];
+#pragma unroll
+    for (int b = 0; b < GR_MAXD / 32; ++b) {
+        const int d = lane + 32 * b;
+        key[b] = -1;
+        if (d < D) {
+            const uint32_t m = s_rows[w][d];
+            const uint32_t tm = ((m & 0xffu) != 0) | (((m >> 8) & 0xffu) != 0) << 1 | (((m >> 16) & 0xffu) != 0) << 2 | ((m >> 24) != 0) << 3;
+            key[b] = (__ffs(tm) - 1) * 4 + (31 - __clz(tm));
+        }
+    }
+    int base = 0;
+    for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int b = 0; b < GR_MAXD / 32; ++b) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, key[b] == k);
+            if (key[b] == k) s_pos[w][lane + 32 * b] = (unsigned char)(base + __popc(bal & ((1u << lane) - 1u)));
+            base += __popc(bal);
+        }
+    __syncwarp();
+    const int4 item = items[it];
+    const int nch = item.z - item.y;
+    unsigned char *rec0 = chunks + (size_t)item.y * GR_REC;
+    // headers and zeroed tables
+    for (int q = 0; q < nch; ++q) {
+        unsigned char *rec = rec0 + (size_t)q * GR_REC;
+        int32_t *h = reinterpret_cast<int32_t *>(rec);
+        // ncols counts whole k-steps: the slots past the last column repeat it with zero coefficients and an empty row
+        // mask, so that the kernel never multiplies stale shared memory
+        const int ncq = max(0, min(GR_CH, D - q * GR_CH));
+        if (lane < 4) h[lane] = lane == 0 ? (ncq + 3) / 4 * 4 : 0;
+        if (lane < 2 * GR_CH) h[4 + lane] = (lane < GR_CH && lane >= ncq && ncq > 0) ? s_cols[w][0] : 0;   // cols and row masks
+        double *cf = reinterpret_cast<double *>(rec + GR_OFF_COEF);
+        for (int k = lane; k < GR_CH * GR_R; k += 32) cf[k] = 0.0;
+    }
+    __syncwarp();
+    for (int d = lane; d < D; d += 32) {
+        const int p = s_pos[w][d];
+        unsigned char *rec = rec0 + (size_t)(p / GR_CH) * GR_REC;
+        const int k = p % GR_CH;
+        const uint32_t m = s_rows[w][d];
+        reinterpret_cast<int32_t *>(rec + GR_OFF_COLS)[k] = s_cols[w][d];
+        reinterpret_cast<uint32_t *>(rec + GR_OFF_RMASK)[k] = m;
+        const uint32_t tm = ((m & 0xffu) != 0) | (((m >> 8) & 0xffu) != 0) << 1 | (((m >> 16) & 0xffu) != 0) << 2 | ((m >> 24) != 0) << 3;
+        atomicOr(reinterpret_cast<int32_t *>(rec) + 1, (int)(tm << (4 * (k / 4))));
+    }
+    // header word 2: the m-tiles whose last column lies in this chunk (their rows are complete and can be written)
+    {
+        int last[4] = {-1, -1, -1, -1};
+        for (int d = lane; d < D; d += 32) {
+            const uint32_t m = s_rows[w][d];
+            const int p = s_pos[w][d];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if ((m >> (8 * t)) & 0xffu) last[t] = max(last[t], p);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int lt = __reduce_max_sync(0xffffffffu, last[t]);
+            if (lane == 0) atomicOr(reinterpret_cast<int32_t *>(rec0 + (size_t)(lt < 0 ? nch - 1 : lt / GR_CH) * GR_REC) + 2, 1 << t);
+        }
+    }
+    // coefficients: lane = row; A-fragment order: [k-step][m-tile][(row % 8) * 4 + column % 4]
+    for (int32_t e = jb; e < je; ++e) {
+        const int32_t c = col[e];
+        int lo = 0, hi = D;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cols[w][mid] < c) lo = mid + 1; else hi = mid; }
+        if (lo >= D) continue;                               // only for a refused item
+        const int p = s_pos[w][lo];
+        double *cf = reinterpret_cast<double *>(rec0 + (size_t)(p / GR_CH) * GR_REC + GR_OFF_COEF);
+        const int k = p % GR_CH;
+        // duplicate (row, column) entries add up, in storage order (a row belongs to one lane)
+        cf[(k / 4) * (4 * 32) + (lane / 8) * 32 + (lane % 8) * 4 + (k % 4)] += val[e];
+    }
+}
 
 static bool make_group_plan(Weighted &W, cudaStream_t s)
 {
@@ -113,183 +196,330 @@ static bool make_group_plan(Weighted &W, cudaStream_t s)
     P.tried = true;
     if (W.nrow < 4 * GR_R || W.nnz < 4 * W.nrow || W.nrow < 4 * W.ncol || W.nnz >= (int64_t(1) << 31)) return false;
     const int64_t nitems = cdiv(W.nrow, GR_R);
-    DBuf<int> wide(1, s);
-    wide.zero();
+    DBuf<int> refuse(1, s);
+    refuse.zero();
+    DBuf<uint32_t> counts((size_t)nitems, s);
+    gr_count_kernel<<<(unsigned)cdiv(nitems, 4), 128, 0, s>>>(W.rowptr.p, W.col.p, W.nrow, nitems, counts.p, refuse.p);
+    IB_LAUNCHED();
     ScanState<uint32_t> st;
-    GrCountLoad L{W.rowptr.p, W.col.p, W.nrow, wide.p};
+    GrCountLoad L{counts.p};
     transform_scan<uint32_t>(st, nitems, L, AddU32{}, 0u, s);
     uint32_t nch = 0;
-    int hwide = 0;
+    int hrefuse = 0;
     IB_CUDA(cudaMemcpyAsync(&nch, st.total.p, sizeof nch, cudaMemcpyDeviceToHost, s));
-    wide.download(&hwide, 1);
+    refuse.download(&hrefuse, 1);
     IB_CUDA(cudaStreamSynchronize(s));
-    // too many distinct columns per 16 rows, or tables much larger than the matrix: the rows do not share columns
-    if (hwide || (int64_t)nch * GR_REC > 6 * 12 * W.nnz + (64 << 10)) return false;
+    // too many distinct columns per 32 rows (or unsorted rows), or tables much larger than the matrix: the rows do not
+    // share columns
+    if (hrefuse || (int64_t)nch * GR_REC > 6 * 12 * W.nnz + (64 << 10)) return false;
     P.nitems = nitems;
     P.nchunks = nch;
     P.items.alloc((size_t)nitems, s);
     P.chunks.alloc((size_t)nch * GR_REC, s);
-    scan_apply<uint32_t>(st, L, AddU32{}, 0u, GrEmit{W.rowptr.p, W.col.p, W.val.p, W.nrow, P.items.p, P.chunks.p}, s);
+    scan_apply<uint32_t>(st, L, AddU32{}, 0u, GrItemEmit{P.items.p, W.nrow}, s);
+    gr_emit_kernel<<<(unsigned)cdiv(nitems, 4), 128, 0, s>>>(W.rowptr.p, W.col.p, W.val.p, W.nrow, nitems, P.items.p, P.chunks.p);
+    IB_LAUNCHED();
     IB_CUDA(cudaStreamSynchronize(s));
     P.ok = true;
     return true;
 }
 
-// ---- kernel: the ring of spmm_stream_kernel -- a producer warp feeds stages (= chunks) to up to eight consumer warps
+// CTA b of `grid` owns the items of [item_lo, item_hi) whose first chunk lies in its share of the chunk range (done once
+// per row block: twenty dependent loads at the head of every CTA cost 15 us per launch when the kernel searched itself)
+__global__ void gr_split_kernel(const int4 *__restrict__ items, int64_t item_lo, int64_t item_hi, int grid, int *__restrict__ split)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > grid) return;
+    const int64_t c_lo = items[item_lo].y, c_hi = items[item_hi - 1].z;
+    const int64_t c = c_lo + (c_hi - c_lo) * b / grid;
+    int64_t lo = item_lo, hi = item_hi;                      // first item whose first chunk >= c
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (items[mid].y < c) lo = mid + 1; else hi = mid; }
+    split[b] = b == grid ? (int)item_hi : (int)lo;
+}
+
+// ---- kernel: the ring of spmm_stream_kernel -- a producer warp feeds stages (= chunks) to up to 16 consumer warps
 struct GrArgs {
     const int4 *items;
     const unsigned char *chunks;
-    int64_t nitems;
+    const int *split;              // [gridDim.x + 1] first item of every CTA
     int ntile, tw, nstage;
     const double *X;
     int64_t ldx;
     int nvar;
     double *Y;
     int64_t ldy;
-    int row_lo, row_hi;
 };
 
-__global__ void __launch_bounds__(288, 2) smooth_group_kernel(const GrArgs a)
+#ifdef IB_GROUP_TRACE       // tools/build_variants.py: per-warp cycle counts of the last launch (never in the product library)
+__device__ unsigned long long g_group_trace[256 * 17 * 6];      // warp 16 = producer
+#define GTR_DECL unsigned long long tr_wait = 0, tr_math = 0, tr_store = 0, tr_pre = 0, tr_g0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_g0)); const long long tr_t0 = clock64(); long long tr_t = tr_t0
+#define GTR_ADD(acc) do { const long long now_ = clock64(); acc += now_ - tr_t; tr_t = now_; } while (0)
+#define GTR_FLUSH() do { if (lane == 0 && blockIdx.x < 256) { unsigned long long *o_ = g_group_trace + ((size_t)blockIdx.x * 17 + warp) * 6; o_[4] = tr_pre; { unsigned long long g1_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1_)); o_[5] = g1_ - tr_g0; } \
+    o_[0] = tr_wait; o_[1] = tr_math; o_[2] = tr_store; o_[3] = clock64() - tr_t0; } } while (0)
+#else
+#define GTR_DECL do { } while (0)
+#define GTR_ADD(acc) do { } while (0)
+#define GTR_FLUSH() do { } while (0)
+#endif
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// The DMMAs of the non-empty blocks (bit t of M: m-tile t) of one k-step.  Selected by a switch over the 16 masks rather
+// than a predicate per block: a predicated-off DMMA still occupies the pipe (ncu: the pipe was busy for the DENSE count).
+template <int M>
+__device__ __forceinline__ void gr_blocks(double (&acc)[4][4][2], const double (&av)[4], const double (&b)[4])
+{
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (M >> t & 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[t][j][0], acc[t][j][1], av[t], b[j]);
+        }
+}
+__device__ __forceinline__ bool gr_finite(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
+
+// Launched with GR_THREADS threads: warps 0..15 consume (those past ncw retire at once), warp 16 produces, warps 17..19
+// only make its warpgroup whole.  Seventeen working warps would cap every thread at 96 registers (five warps on one
+// scheduler); the producer's warpgroup hands its registers back (setmaxnreg) so that the consumers, which hold 64
+// accumulator registers each, run with 112.
+constexpr int GR_THREADS = 640;
+__global__ void __launch_bounds__(GR_THREADS, 1) smooth_group_kernel(const __grid_constant__ GrArgs a)
 {
     extern __shared__ __align__(128) unsigned char gr_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(gr_raw);
     uint64_t *empty = full + a.nstage;
     unsigned char *data = gr_raw + 128;
-    const uint32_t rowbytes = (uint32_t)a.tw * 8u;
-    const uint32_t stagebytes = rowbytes * GR_CH + GR_REC;
+    const uint32_t rowstride = (uint32_t)a.tw * 8u + GR_SKEW;
+    const uint32_t stagebytes = rowstride * GR_CH + GR_REC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncw = (int)(blockDim.x >> 5) - 1;
+    const int ncw = a.tw / 32;
     if (threadIdx.x == 0) {
         for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, ncw); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // contiguous share of the (item, tile) units, item-major: a CTA walks neighbouring items (their X rows overlap in L2)
-    const int64_t nunits = a.nitems * a.ntile;
-    const int64_t u0 = nunits * blockIdx.x / gridDim.x, u1 = nunits * (blockIdx.x + 1) / gridDim.x;
+    // a contiguous share of the items, balanced by their chunks (gr_split_kernel; a CTA walks neighbouring items: their
+    // X rows overlap in L2)
+    const int64_t i0 = __ldg(a.split + blockIdx.x), i1 = __ldg(a.split + blockIdx.x + 1);
     int stage = 0;
     uint32_t phase = 0;
-    auto in_block = [&](const int4 &it) { return it.x >= a.row_lo && it.x < a.row_hi; };
-    if (warp == ncw) {
+    if (warp >= 16) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (warp > 16 || i0 >= i1) return;
         // ===== producer: one stage per chunk; lane k < ncols copies the X row of column k, lane 31 the chunk record.
         // The column ids of a stage are loaded one stage ahead, so the only thing the producer ever waits for is a
         // free stage.
-        int64_t u = u0;
-        int4 it = make_int4(0, 0, 0, 0);
-        while (u < u1 && !in_block(it = __ldg(a.items + u / a.ntile))) ++u;
-        if (u >= u1) return;
-        int q = it.y;
-        auto meta = [&](int qq, int &nc, int32_t &c) {
-            const unsigned char *rec = a.chunks + (size_t)qq * GR_REC;
-            nc = __ldg(reinterpret_cast<const int32_t *>(rec));
-            c = lane < GR_CH ? __ldg(reinterpret_cast<const int32_t *>(rec + GR_OFF_COLS) + lane) : 0;
-        };
-        int nc;
-        int32_t c;
-        meta(q, nc, c);
-        while (u < u1) {
-            // the stage after this one
-            int64_t un = u;
-            int4 itn = it;
-            int qn = q + 1;
-            if (qn >= it.z) {
-                ++un;
-                while (un < u1 && !in_block(itn = __ldg(a.items + un / a.ntile))) ++un;
-                qn = itn.y;
-            }
-            int ncn = 0;
-            int32_t cn = 0;
-            if (un < u1) meta(qn, ncn, cn);
-            const int f0 = (int)(u % a.ntile) * a.tw;
+        GTR_DECL;
+        for (int tile = 0; tile < a.ntile; ++tile) {
+            const int f0 = tile * a.tw;
             const uint32_t tb = (uint32_t)min(a.tw, a.nvar - f0) * 8u;
-            unsigned char *sp = data + (size_t)stage * stagebytes;
-            if (lane == 0) {
-                mbar_wait(empty + stage, phase ^ 1u);
-                mbar_expect_tx(full + stage, tb * (uint32_t)nc + GR_REC);
+            const int q0 = __ldg(a.items + i0).y, q1 = __ldg(a.items + i1 - 1).z;
+            // metadata of FOUR chunks per load (lane = 8 * chunk + column slot), fetched a group ahead: the producer's
+            // own loads were what paced it when it looked one chunk ahead (a dependent L2 round trip per stage)
+            const int jq = lane >> 3, k = lane & 7;
+            auto meta = [&](int qg, int &nc, int32_t &c) {
+                nc = 0; c = 0;
+                if (qg + jq < q1) {
+                    const unsigned char *rec = a.chunks + (size_t)(qg + jq) * GR_REC;
+                    nc = __ldg(reinterpret_cast<const int32_t *>(rec));
+                    c = __ldg(reinterpret_cast<const int32_t *>(rec + GR_OFF_COLS) + k);
+                }
+            };
+            int nc4;
+            int32_t c;
+            meta(q0, nc4, c);
+            for (int qg = q0; qg < q1; qg += 4) {
+                int nc4n;
+                int32_t cn;
+                meta(qg + 4, nc4n, cn);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int q = qg + jj;
+                    if (q >= q1) break;
+                    const int nc = __shfl_sync(0xffffffffu, nc4, 8 * jj);
+                    unsigned char *sp = data + (size_t)stage * stagebytes;
+                    GTR_ADD(tr_math);
+                    if (lane == 0) {
+                        mbar_wait(empty + stage, phase ^ 1u);
+                        mbar_expect_tx(full + stage, tb * (uint32_t)nc + GR_REC);
+                    }
+                    __syncwarp();
+                    GTR_ADD(tr_wait);
+                    if (jq == jj && k < nc) bulk_g2s(sp + (size_t)k * rowstride, a.X + (int64_t)c * a.ldx + f0, tb, full + stage);
+                    if (lane == 8 * ((jj + 1) & 3)) bulk_g2s(sp + (size_t)GR_CH * rowstride, a.chunks + (size_t)q * GR_REC, GR_REC, full + stage);
+                    if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
+                }
+                nc4 = nc4n; c = cn;
             }
-            __syncwarp();
-            if (lane < nc) bulk_g2s(sp + (size_t)lane * rowbytes, a.X + (int64_t)c * a.ldx + f0, tb, full + stage);
-            if (lane == 31) bulk_g2s(sp + (size_t)GR_CH * rowbytes, a.chunks + (size_t)q * GR_REC, GR_REC, full + stage);
-            if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
-            u = un; it = itn; q = qn; nc = ncn; c = cn;
         }
+        GTR_FLUSH();
         return;
     }
-    // ===== consumers: lane owns fields f0 + 64*warp + 2*lane, +1 of all 16 rows of the item
-    const int fo = 64 * warp + 2 * lane;
-    double2 acc[GR_R];
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    if (warp >= ncw || i0 >= i1) return;
+    // ===== consumers: warp w owns fields f0 + 32 w .. + 31 of all 32 rows of the item: acc[m-tile][n-tile] in DMMA
+    // C-fragment layout (row 8 t + lane / 4, fields 8 j + 2 (lane % 4), + 1)
+    const int fo = 32 * warp;
+    const int g = lane >> 2, q4 = lane & 3;
+    double acc[4][4][2];
+    GTR_DECL;
+    for (int tile = 0; tile < a.ntile; ++tile) {
+        const int f0 = tile * a.tw;
+        const int nf = min(a.tw, a.nvar - f0);               // fields of this tile
+        const bool fields_full = fo + 32 <= nf;
+        for (int64_t i = i0; i < i1; ++i) {
+            const int4 it = __ldg(a.items + i);
+            double *y = a.Y + (int64_t)it.x * a.ldy + f0 + fo + 2 * q4;
 #pragma unroll
-    for (int r = 0; r < GR_R; ++r) acc[r] = make_double2(0.0, 0.0);
-    int4 it_next = u0 < u1 ? __ldg(a.items + u0 / a.ntile) : make_int4(0, 0, 0, 0);
-    for (int64_t u = u0; u < u1; ++u) {
-        const int4 it = it_next;
-        if (u + 1 < u1) it_next = __ldg(a.items + (u + 1) / a.ntile);
-        if (!in_block(it)) continue;
-        const int f0 = (int)(u % a.ntile) * a.tw;
-        for (int q = it.y; q < it.z; ++q) {
-            mbar_wait(full + stage, phase);
-            const unsigned char *sb = data + (size_t)stage * stagebytes;
-            const unsigned char *rec = sb + (size_t)GR_CH * rowbytes;
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[t][j][0] = acc[t][j][1] = 0.0;
+            for (int q = it.y; q < it.z; ++q) {
+                GTR_ADD(tr_math);
+                mbar_wait(full + stage, phase);
+                GTR_ADD(tr_wait);
+                const unsigned char *sb = data + (size_t)stage * stagebytes;
+                const unsigned char *rec = sb + (size_t)GR_CH * rowstride;
+                // header: ncols (whole k-steps), block mask, done mask -- one 16-byte load
+                const int4 hdr = *reinterpret_cast<const int4 *>(rec);
 #ifdef IB_GROUP_SKIP_MATH       // tools/: delivery rate of the ring alone (results are wrong)
-            const int nc = 0;
+                const int nc = 0;
 #else
-            const int nc = *reinterpret_cast<const int32_t *>(rec);
+                const int nc = hdr.x;
 #endif
-            const unsigned char *xs = sb + (size_t)fo * 8;
-#pragma unroll 2
-            for (int c = 0; c < nc; ++c) {
-                const double2 x = *reinterpret_cast<const double2 *>(xs + (size_t)c * rowbytes);
-                const double2 *cf = reinterpret_cast<const double2 *>(rec + GR_OFF_COEF + c * (8 * GR_R));
-                // A row that does not name this column has coefficient 0 in the table; 0 * x adds nothing as long as x is
-                // finite.  Only if some lane holds a NaN / Inf here (a masked field value) do the presence bits decide.
-                const bool finite = ((__double2hiint(x.x) & 0x7ff00000) != 0x7ff00000) && ((__double2hiint(x.y) & 0x7ff00000) != 0x7ff00000);
-                if (__all_sync(0xffffffffu, finite)) {
+                const uint32_t bm = (uint32_t)hdr.y;
+                const double *cf = reinterpret_cast<const double *>(rec + GR_OFF_COEF);
+                if (nc > 0) {
+                    // all fragments of the chunk before the first DMMA.  B: X[column 4 s + lane % 4][field fo + 8 j +
+                    // lane / 4]; A: the four m-tiles of each k-step (empty blocks hold zeros).  The second k-step's X
+                    // rows exist only if the chunk has more than four columns.
+                    const unsigned char *xb = sb + (size_t)q4 * rowstride + (size_t)(fo + g) * 8;
+                    const bool two = nc > 4;
+                    double b[2][4], av[4];
 #pragma unroll
-                    for (int r2 = 0; r2 < GR_R / 2; ++r2) {
-                        const double2 v = cf[r2];                         // coefficients of rows 2*r2, 2*r2 + 1
-                        acc[2 * r2].x = fma(v.x, x.x, acc[2 * r2].x); acc[2 * r2].y = fma(v.x, x.y, acc[2 * r2].y);
-                        acc[2 * r2 + 1].x = fma(v.y, x.x, acc[2 * r2 + 1].x); acc[2 * r2 + 1].y = fma(v.y, x.y, acc[2 * r2 + 1].y);
+                    for (int j = 0; j < 4; ++j) {
+                        b[0][j] = *reinterpret_cast<const double *>(xb + 64 * j);
+                        b[1][j] = two ? *reinterpret_cast<const double *>(xb + 4 * (size_t)rowstride + 64 * j) : 0.0;
                     }
-                } else {
-                    const uint32_t m = *reinterpret_cast<const uint16_t *>(rec + GR_OFF_MASK + 2 * c);
-#pragma unroll 1
-                    for (int r2 = 0; r2 < GR_R / 2; ++r2) {
-                        const double2 v = cf[r2];
-                        const bool p0 = m >> (2 * r2) & 1u, p1 = m >> (2 * r2 + 1) & 1u;
 #pragma unroll
-                        for (int k = 0; k < GR_R / 2; ++k) {              // static register indices: select the pair k == r2
-                            if (k == r2) {
-                                if (p0) { acc[2 * k].x = fma(v.x, x.x, acc[2 * k].x); acc[2 * k].y = fma(v.x, x.y, acc[2 * k].y); }
-                                if (p1) { acc[2 * k + 1].x = fma(v.y, x.x, acc[2 * k + 1].x); acc[2 * k + 1].y = fma(v.y, x.y, acc[2 * k + 1].y); }
+                    for (int t = 0; t < 4; ++t) av[t] = cf[t * 32 + lane];
+#ifdef IB_GROUP_AV_EARLY
+                    double av1[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) av1[t] = cf[(4 + t) * 32 + lane];
+#endif
+                    if (!fields_full) {
+                        // fields past nvar were not copied: stale shared memory
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (fo + 8 * j + g >= nf) b[0][j] = b[1][j] = 0.0;
+                    }
+#ifdef IB_GROUP_NOCHECK         // tools/: cost of the NaN / Inf check (results are wrong for non-finite input)
+                    const bool fin = true;
+#else
+                    bool fin = true;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) fin = fin && gr_finite(b[0][j]) && gr_finite(b[1][j]);
+#endif
+                    const bool allfin = __all_sync(0xffffffffu, fin);
+                    GTR_ADD(tr_pre);
+                    if (allfin) {
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) {
+                            // the second k-step's A fragments take the registers of the first's once its DMMAs are issued
+                            if (s == 1) {
+#pragma unroll
+#ifdef IB_GROUP_AV_EARLY
+                                for (int t = 0; t < 4; ++t) av[t] = av1[t];
+#else
+                                for (int t = 0; t < 4; ++t) av[t] = cf[(4 + t) * 32 + lane];
+#endif
+                            }
+                            switch (bm >> (4 * s) & 15u) {
+                            case 1: gr_blocks<1>(acc, av, b[s]); break;
+                            case 2: gr_blocks<2>(acc, av, b[s]); break;
+                            case 3: gr_blocks<3>(acc, av, b[s]); break;
+                            case 4: gr_blocks<4>(acc, av, b[s]); break;
+                            case 5: gr_blocks<5>(acc, av, b[s]); break;
+                            case 6: gr_blocks<6>(acc, av, b[s]); break;
+                            case 7: gr_blocks<7>(acc, av, b[s]); break;
+                            case 8: gr_blocks<8>(acc, av, b[s]); break;
+                            case 9: gr_blocks<9>(acc, av, b[s]); break;
+                            case 10: gr_blocks<10>(acc, av, b[s]); break;
+                            case 11: gr_blocks<11>(acc, av, b[s]); break;
+                            case 12: gr_blocks<12>(acc, av, b[s]); break;
+                            case 13: gr_blocks<13>(acc, av, b[s]); break;
+                            case 14: gr_blocks<14>(acc, av, b[s]); break;
+                            case 15: gr_blocks<15>(acc, av, b[s]); break;
+                            default: break;
+                            }
+                        }
+                    } else {
+                        // a NaN / Inf among the X values: only the rows that name a column may see it
+#pragma unroll 1
+                        for (int c = 0; c < nc; ++c) {
+                            const uint32_t rm = *reinterpret_cast<const uint32_t *>(rec + GR_OFF_RMASK + 4 * c);
+                            const unsigned char *xr = sb + (size_t)c * rowstride + (size_t)(fo + 2 * q4) * 8;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                double2 x = *reinterpret_cast<const double2 *>(xr + 64 * j);
+                                if (fo + 8 * j + 2 * q4 >= nf) x = make_double2(0.0, 0.0);
+#pragma unroll
+                                for (int t = 0; t < 4; ++t)
+                                    if (rm >> (8 * t + g) & 1u) {
+                                        const double v = cf[((c >> 2) * 4 + t) * 32 + g * 4 + (c & 3)];
+                                        acc[t][j][0] = fma(v, x.x, acc[t][j][0]);
+                                        acc[t][j][1] = fma(v, x.y, acc[t][j][1]);
+                                    }
                             }
                         }
                     }
                 }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + stage);
-            if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
-        }
-        const int f = f0 + fo;
+                const uint32_t done = (uint32_t)hdr.z;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + stage);
+                if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
+                // the m-tiles that end with this chunk are written now (8 rows x 256 bytes per warp), spreading the
+                // output over the item instead of one burst of 16 stores per warp at its end; no later block of the
+                // item touches their accumulators, which are cleared with all the others when the next item starts
+                if (done) {
+                    GTR_ADD(tr_math);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        if (done >> t & 1u) {
 #ifdef IB_GROUP_SKIP_STORE      // tools/: the ring without its output (results are wrong)
-        if (acc[0].x == 12345.678 && fo < a.tw && f < a.nvar) {
-#else
-        if (fo < a.tw && f < a.nvar) {
+                            if (acc[0][0][0] == 12345.678)
 #endif
-            double *y = a.Y + (int64_t)it.x * a.ldy + f;
+                            if (8 * t + g < it.w) {
 #pragma unroll
-            for (int r = 0; r < GR_R; ++r)
-                if (r < it.w) *reinterpret_cast<double2 *>(y + (int64_t)r * a.ldy) = acc[r];
+                                for (int j = 0; j < 4; ++j)
+                                    if (fo + 8 * j + 2 * q4 < nf)
+                                        *reinterpret_cast<double2 *>(y + (int64_t)(8 * t + g) * a.ldy + 8 * j) = make_double2(acc[t][j][0], acc[t][j][1]);
+                            }
+                        }
+                    GTR_ADD(tr_store);
+                }
+            }
         }
-#pragma unroll
-        for (int r = 0; r < GR_R; ++r) acc[r] = make_double2(0.0, 0.0);
     }
+    GTR_FLUSH();
 }
+
+#ifdef IB_GROUP_TRACE
+extern "C" int ib_debug_group_trace(unsigned long long *out, int nblk)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_group_trace, sizeof(unsigned long long) * 17 * 6 * nblk);
+}
+#endif
 
 // Applies W through the group kernel; false (nothing launched) if the matrix does not fit it.
 bool apply_group(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY, int64_t ldy, int row_lo, int row_hi, cudaStream_t s)
 {
     if (nvar < 32 || nvar % 2 || ldx % 2 || ldy % 2 || (uintptr_t)dX % 16 || (uintptr_t)dY % 16) return false;
+    if (row_lo % GR_R) return false;
     if (!make_group_plan(W, s)) return false;
     GroupPlan &P = W.group_plan;
     static int max_smem[IB_MAX_DEVICES] = {};
@@ -304,22 +534,25 @@ bool apply_group(Weighted &W, const double *dX, int64_t ldx, int nvar, double *d
             max_smem[dev] = ms;
         }
     }
-    // X rows travel as ONE bulk copy per column and tile (the copy engine handles ~1 copy per 50 ns and SM: 512-byte
-    // pieces made it the bottleneck), so tiles are as wide as possible: up to 512 fields = 8 consumer warps
-    const int tw = std::min((nvar + 63) / 64 * 64, 512);
+    // X rows travel as ONE bulk copy per column and tile (the copy engine handles ~1 copy per 60 ns and SM: small
+    // pieces made it the bottleneck), so tiles are as wide as possible: up to 512 fields = 16 consumer warps, one CTA per SM
+    const int tw = std::min((nvar + 31) / 32 * 32, 512);
     const int ntile = (nvar + tw - 1) / tw;
-    const int ncw = tw / 64;
-    const size_t stagebytes = (size_t)tw * 8 * GR_CH + GR_REC;
-    // two CTAs per SM: 16 consumer warps keep the fp64 pipe busy (with 8, a warp's own DFMA issue interval left it half idle)
-    const int nstage = (int)std::min<size_t>(8, ((size_t)(max_smem[dev] + 1024) / 2 - 1024 - 128) / stagebytes);
+    const size_t stagebytes = ((size_t)tw * 8 + GR_SKEW) * GR_CH + GR_REC;
+    const int nstage = (int)std::min<size_t>(8, ((size_t)max_smem[dev] - 128) / stagebytes);
     if (nstage < 2) return false;
     const size_t smem = 128 + (size_t)nstage * stagebytes;
-    GrArgs a{P.items.p, P.chunks.p, P.nitems, ntile, tw, nstage, dX, ldx, nvar, dY, ldy, row_lo, row_hi};
-    int occ = 0;
-    IB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smooth_group_kernel, 32 * (ncw + 1), smem));
-    if (occ < 1) return false;
-    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(P.nitems * ntile, (int64_t)sm_count() * std::min(occ, 2)));
-    smooth_group_kernel<<<(unsigned)grid, 32 * (ncw + 1), smem, s>>>(a);
+    const int64_t item_lo = row_lo / GR_R, item_hi = std::min<int64_t>(P.nitems, cdiv(row_hi, GR_R));
+    if (item_lo >= item_hi) return true;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(item_hi - item_lo, sm_count()));
+    if (P.split_lo != item_lo || P.split_hi != item_hi || P.split_grid != (int)grid) {
+        P.split.alloc((size_t)grid + 1, s);
+        gr_split_kernel<<<(unsigned)cdiv(grid + 1, 128), 128, 0, s>>>(P.items.p, item_lo, item_hi, (int)grid, P.split.p);
+        IB_LAUNCHED();
+        P.split_lo = item_lo; P.split_hi = item_hi; P.split_grid = (int)grid;
+    }
+    GrArgs a{P.items.p, P.chunks.p, P.split.p, ntile, tw, nstage, dX, ldx, nvar, dY, ldy};
+    smooth_group_kernel<<<(unsigned)grid, GR_THREADS, smem, s>>>(a);
     IB_LAUNCHED();
     return true;
 }

@@ -111,6 +111,9 @@ struct GroupPlan {
     int64_t nitems = 0, nchunks = 0;
     DBuf<int4> items;               // (first row, first chunk, end chunk, rows)
     DBuf<unsigned char> chunks;     // chunk records: columns, presence masks, dense coefficient table
+    DBuf<int> split;                // [split_grid + 1] first item of every CTA for the row block [split_lo, split_hi)
+    int64_t split_lo = -1, split_hi = -1;
+    int split_grid = 0;
 };
 
 uint64_t next_uid();

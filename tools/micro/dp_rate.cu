@@ -41,6 +41,24 @@ __global__ void lds_kernel(double *out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y;
 }
 
+// fp64 tensor-core rate: mma.sync.m8n8k4.f64, NT independent accumulator tiles per warp
+template <int NT>
+__global__ void dmma_kernel(double *out, double a, double b, int iters)
+{
+    double c0[NT], c1[NT];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) { c0[k] = threadIdx.x * 1e-3 + k; c1[k] = k; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < NT; ++k)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[k]), "+d"(c1[k]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < NT; ++k) s += c0[k] + c1[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main()
 {
     int sms = 0;
@@ -64,6 +82,19 @@ int main()
                             ops / ms / 1e9, ops / ms / 1e9 * 1e12 / sms / 1.9e9 / 1e12 * 1.0, (mode == 0 ? 2 : 1) * ops / ms / 1e9);
         }
     }
+    for (int nt = 0; nt < 2; ++nt)
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0);
+            if (nt == 0) dmma_kernel<8><<<sms * 8, 256>>>(out, 1.0000001, 1e-9, iters / 4);
+            else dmma_kernel<16><<<sms * 4, 256>>>(out, 1.0000001, 1e-9, iters / 4);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            double mmas = (double)sms * (nt == 0 ? 8 : 4) * 8 * (nt == 0 ? 8 : 16) * (iters / 4);      // warp-level instructions
+            if (rep) printf("DMMA m8n8k4 (%d tiles/warp): %.3f ms, %.2f G mma/s, %.2f TFLOP/s (%.2f mma per clk per SM at 1.9 GHz)\n", nt == 0 ? 8 : 16, ms,
+                            mmas / ms / 1e6, mmas * 512 / ms / 1e9, mmas / ms / 1e6 * 1e9 / sms / 1.9e9);
+        }
     for (int rep = 0; rep < 2; ++rep) {
         cudaEventRecord(e0);
         lds_kernel<<<sms * 4, 256, 65536>>>(out, iters);
