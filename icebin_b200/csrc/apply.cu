@@ -712,22 +712,24 @@ __global__ void __launch_bounds__(256) spmm_fixup_kernel(const int4 *__restrict_
 }
 
 // ---- conservation correction (ibmisc Weighted_Eigen::apply_e; matrix_formats.rst:156-165) ---------------
-// The whole correction of the input in ONE launch: a block owns 8 fields and walks ALL rows twice.  Pass 1: thread
-// (rg, fi) adds up rows rg, rg + 64, ... of field fi for both weight vectors (independent 64-byte-coalesced loads, all in
-// flight at once at 1120 rows); the 64 row groups are added in order through shared memory (deterministic):
-// factor[f] = (wa . A)[f] / (wb . A)[f].  Pass 2: As[r][f] = A[r][f] * factor[f] (the rows are still in L1 / L2).
+// The whole correction of the input in ONE launch: a block owns 4 fields (one 32-byte sector per row) and walks ALL
+// rows twice.  Pass 1: thread (rg, fi) adds up rows rg, rg + 128, ... of field fi for both weight vectors (nine
+// independent loads at 1120 rows, all in flight at once); the 128 row groups are added in a fixed order through shared
+// memory (deterministic): factor[f] = (wa . A)[f] / (wb . A)[f].  Pass 2: As[r][f] = A[r][f] * factor[f] (the rows are
+// still in L1 / L2).  128 blocks at 512 fields: one per SM.
 __global__ void __launch_bounds__(512) cons_scale_kernel(const double *__restrict__ wa, const double *__restrict__ wb,
                                                          const double *__restrict__ A, int64_t lda, int64_t nrow, int nvar,
                                                          double *__restrict__ As, int64_t ldas)
 {
-    __shared__ double sa_s[64][8], sb_s[64][8];
-    __shared__ double fac_s[8];
-    const int rg = threadIdx.x >> 3, fi = threadIdx.x & 7;
-    const int f = blockIdx.x * 8 + fi;
+    __shared__ double sa_s[128][4], sb_s[128][4];
+    __shared__ double pa_s[8][4], pb_s[8][4];
+    __shared__ double fac_s[4];
+    const int rg = threadIdx.x >> 2, fi = threadIdx.x & 3;
+    const int f = blockIdx.x * 4 + fi;
     double sa = 0, sb = 0;
     if (f < nvar) {
-#pragma unroll 4
-        for (int64_t r = rg; r < nrow; r += 64) {
+#pragma unroll 9
+        for (int64_t r = rg; r < nrow; r += 128) {
             const double x = A[r * lda + f];
             sa = sa + __ldg(wa + r) * x;
             sb = sb + __ldg(wb + r) * x;
@@ -736,17 +738,26 @@ __global__ void __launch_bounds__(512) cons_scale_kernel(const double *__restric
     sa_s[rg][fi] = sa;
     sb_s[rg][fi] = sb;
     __syncthreads();
-    if (threadIdx.x < 8) {
+    if (threadIdx.x < 32) {                              // 8 runs of 16 row groups per field, then the 8 runs
+        const int run = threadIdx.x >> 2;
         double ta = 0, tb = 0;
 #pragma unroll
-        for (int g = 0; g < 64; ++g) { ta = ta + sa_s[g][fi]; tb = tb + sb_s[g][fi]; }
+        for (int g = 0; g < 16; ++g) { ta = ta + sa_s[run * 16 + g][fi]; tb = tb + sb_s[run * 16 + g][fi]; }
+        pa_s[run][fi] = ta;
+        pb_s[run][fi] = tb;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double ta = 0, tb = 0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { ta = ta + pa_s[g][fi]; tb = tb + pb_s[g][fi]; }
         fac_s[fi] = ta * (1. / tb);
     }
     __syncthreads();
     if (f < nvar) {
         const double fc = fac_s[fi];
-#pragma unroll 4
-        for (int64_t r = rg; r < nrow; r += 64) As[r * ldas + f] = A[r * lda + f] * fc;
+#pragma unroll 9
+        for (int64_t r = rg; r < nrow; r += 128) As[r * ldas + f] = A[r * lda + f] * fc;
     }
 }
 // v[c] = sum_r M[r,c] * wM[r], columns walked in CSC order (rows ascending): deterministic
@@ -854,7 +865,7 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         compute_cons_v(W, s);
         const int64_t ldxs = (nvar + 1) & ~1;
         Xscaled.alloc((size_t)W.ncol * ldxs, s);
-        cons_scale_kernel<<<(unsigned)cdiv(nvar, 8), 512, 0, s>>>(W.Mw.p, W.cons_v.p, dX, ldx, W.ncol, nvar, Xscaled.p, ldxs);
+        cons_scale_kernel<<<(unsigned)cdiv(nvar, 4), 512, 0, s>>>(W.Mw.p, W.cons_v.p, dX, ldx, W.ncol, nvar, Xscaled.p, ldxs);
         IB_LAUNCHED();
         dX = Xscaled.p;
         ldx = ldxs;

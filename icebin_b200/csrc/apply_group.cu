@@ -7,24 +7,33 @@
 // and multiplying with DFMA still costs one shared-memory read per column and 36 LDS.128 per 128 DFMA -- measured 182 us
 // with the fp64 pipe 27 % busy, warps waiting on shared-memory loads (ncu: short scoreboard).  So the product is done as
 // small DENSE blocks on the fp64 tensor-core path (DMMA.8x8x4; B200 measured 72.5 G mma/s = 37 TFLOP/s, the same flops as
-// DFMA but 10 operand loads per 16 mma):
+// DFMA but 8 operand loads per ~10 mma):
 //   item  = 32 consecutive rows = four m-tiles of 8 rows; its distinct columns, ordered by (first, last m-tile that names
-//           them) so that most 8-row x 4-column blocks of the item are either dense or empty, cut into chunks of 8 columns;
+//           them) so that most 8-row x 4-column blocks of the item are either dense or empty (3.3 M DMMA at 5 km against
+//           5.1 M for the dense items), cut into chunks of 8 columns;
 //   chunk = the X rows of its columns (ONE 1-D bulk async copy each: 4 KB at 512 fields) + the coefficients of its
-//           2 k-steps x 4 m-tiles laid out in DMMA A-fragment order, a bit per non-empty block, and a 32-bit row-presence
-//           mask per column; prepared once per matrix; a chunk is one stage of a shared-memory ring fed by a producer warp;
-//   a consumer warp owns a 32-field strip of the item: 4 x 4 accumulator tiles; per k-step 4 B-fragment loads (X), one
-//   A-fragment load and 4 DMMA per non-empty block.  X rows sit 32 bytes apart modulo 128 in shared memory so that the
-//   B-fragment loads (4 rows x 8 fields) are conflict-free.
+//           2 k-steps x 4 m-tiles laid out in DMMA A-fragment order, a bit per non-empty block, a bit per m-tile that
+//           ends here, and a 32-bit row-presence mask per column; prepared once per matrix; a chunk is one stage of a
+//           shared-memory ring fed by a producer warp;
+//   a consumer warp owns a 32-field strip of the item: 4 x 4 accumulator tiles; per chunk 8 B-fragment loads (X), one
+//   A-fragment load and 4 DMMA per non-empty block, selected by a switch over the 16 block masks of a k-step (a
+//   predicated-off DMMA still occupies the pipe).  X rows sit 32 bytes apart modulo 128 in shared memory so that the
+//   B-fragment loads (4 rows x 8 fields) are conflict-free.  An m-tile is written as soon as its last chunk is done.
 // Rows that do not name a column of a non-empty block carry a zero coefficient, which adds nothing while x is finite;
-// where a warp sees a NaN / Inf in the k-step's X values the presence bits take over (scalar FMA path), so a NaN in X
+// where a warp sees a NaN / Inf in the chunk's X values the presence bits take over (scalar FMA path), so a NaN in X
 // reaches only the rows that name its cell (structural zeros are never multiplied into a sum).  The terms of a row are
 // added four columns at a time inside the tensor core, so results agree with the oracle to rounding (1e-12 gate), not bit
 // for bit.
 //
-// Roofline: HBM (Y written once: 12*nnz + 8*nvar*(nrow + ncol) algorithmic bytes); next bounds: the fp64 pipe (3.3 M
-// DMMA at 5 km: 45 us), the bulk-copy engine (one copy per ~60 ns and SM: 1.1 X rows per output row) and L2 -> SM
-// traffic.  (History: every warp its own pipeline with 512-byte copies 380 us -> CTA ring, 16-row items, DFMA 182 us.)
+// Roofline: HBM (Y written once: 12*nnz + 8*nvar*(nrow + ncol) algorithmic bytes).  What a consumer warp's time goes to
+// at 5 km / 512 fields (tools/group_trace.py, 77 us per CTA): DMMA issue on a saturated pipe 45 us (= the 3.3 M DMMA at
+// the measured rate), the loads / checks / addressing ahead of them 19 us (issue-bound: the four warps of a scheduler
+// move in step, so this does not overlap the other warps' DMMA), stores 7 us, waiting for a stage 6 us.  The CTAs get
+// equal shares of a fitted cost (item, chunk, block), 72 .. 85 us; the kernel takes 87 us = 0.53 of the HBM roofline.
+// History: every warp its own pipeline with 512-byte copies 380 us -> CTA ring, 16-row items, DFMA 182 us -> DMMA 139 us
+// -> A fragments before the first DMMA + 112 registers for the consumers (setmaxnreg) 105 us -> switch instead of
+// predicates 102 us -> CTA shares read from a table instead of a binary search at the head of every CTA 99 us -> shares
+// by fitted cost 87 us.
 #include <algorithm>
 #include <mutex>
 
@@ -89,9 +98,15 @@ struct GrItemEmit {
     }
 };
 
+struct GrPrefixEmit {
+    uint32_t *prefix;
+    __device__ void operator()(int64_t it, uint32_t before, uint32_t) const { prefix[it] = before; }
+};
+
 __global__ void __launch_bounds__(128) gr_emit_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                                       const double *__restrict__ val, int64_t nrow, int64_t nitems,
-                                                      const int4 *__restrict__ items, unsigned char *__restrict__ chunks)
+                                                      const int4 *__restrict__ items, unsigned char *__restrict__ chunks,
+                                                      uint32_t *__restrict__ weight)
 {
     __shared__ int32_t s_cols[4][GR_MAXD];
     __shared__ uint32_t s_rows[4][GR_MAXD];
@@ -175,6 +190,17 @@ __global__ void __launch_bounds__(128) gr_emit_kernel(const int32_t *__restrict_
             if (lane == 0) atomicOr(reinterpret_cast<int32_t *>(rec0 + (size_t)(lt < 0 ? nch - 1 : lt / GR_CH) * GR_REC) + 2, 1 << t);
         }
     }
+    // estimated cost of the item, in ns: least-squares fit of the CTAs' lifetimes at 512 fields (tools/group_trace.py)
+    // against their items, chunks and non-empty blocks: 1140 per item (stores, accumulator reset), 491 per chunk (loads,
+    // checks, barriers), 69 per block (4 DMMA on a pipe shared by four warps); residual 1.4 us per CTA
+    {
+        __syncwarp();
+        uint32_t wq = 0;
+        for (int q = lane; q < nch; q += 32)
+            wq += 491u + 69u * (uint32_t)__popc(reinterpret_cast<const int32_t *>(rec0 + (size_t)q * GR_REC)[1]);
+        wq = __reduce_add_sync(0xffffffffu, wq);
+        if (lane == 0) weight[it] = wq + 1140u;
+    }
     // coefficients: lane = row; A-fragment order: [k-step][m-tile][(row % 8) * 4 + column % 4]
     for (int32_t e = jb; e < je; ++e) {
         const int32_t c = col[e];
@@ -217,23 +243,29 @@ static bool make_group_plan(Weighted &W, cudaStream_t s)
     P.items.alloc((size_t)nitems, s);
     P.chunks.alloc((size_t)nch * GR_REC, s);
     scan_apply<uint32_t>(st, L, AddU32{}, 0u, GrItemEmit{P.items.p, W.nrow}, s);
-    gr_emit_kernel<<<(unsigned)cdiv(nitems, 4), 128, 0, s>>>(W.rowptr.p, W.col.p, W.val.p, W.nrow, nitems, P.items.p, P.chunks.p);
+    gr_emit_kernel<<<(unsigned)cdiv(nitems, 4), 128, 0, s>>>(W.rowptr.p, W.col.p, W.val.p, W.nrow, nitems, P.items.p, P.chunks.p, counts.p);
     IB_LAUNCHED();
+    // counts now holds the items' estimated costs; their running sum is what the CTAs split evenly
+    P.wprefix.alloc((size_t)nitems + 1, s);
+    ScanState<uint32_t> sw;
+    transform_scan<uint32_t>(sw, nitems, L, AddU32{}, 0u, s);
+    scan_apply<uint32_t>(sw, L, AddU32{}, 0u, GrPrefixEmit{P.wprefix.p}, s);
+    IB_CUDA(cudaMemcpyAsync(P.wprefix.p + nitems, sw.total.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     IB_CUDA(cudaStreamSynchronize(s));
     P.ok = true;
     return true;
 }
 
-// CTA b of `grid` owns the items of [item_lo, item_hi) whose first chunk lies in its share of the chunk range (done once
+// CTA b of `grid` owns the items of [item_lo, item_hi) that start in its share of the block's estimated cost (done once
 // per row block: twenty dependent loads at the head of every CTA cost 15 us per launch when the kernel searched itself)
-__global__ void gr_split_kernel(const int4 *__restrict__ items, int64_t item_lo, int64_t item_hi, int grid, int *__restrict__ split)
+__global__ void gr_split_kernel(const uint32_t *__restrict__ wprefix, int64_t item_lo, int64_t item_hi, int grid, int *__restrict__ split)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b > grid) return;
-    const int64_t c_lo = items[item_lo].y, c_hi = items[item_hi - 1].z;
-    const int64_t c = c_lo + (c_hi - c_lo) * b / grid;
-    int64_t lo = item_lo, hi = item_hi;                      // first item whose first chunk >= c
-    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (items[mid].y < c) lo = mid + 1; else hi = mid; }
+    const uint64_t w_lo = wprefix[item_lo], w_hi = wprefix[item_hi];
+    const uint64_t w = w_lo + (w_hi - w_lo) * (uint64_t)b / (uint64_t)grid;
+    int64_t lo = item_lo, hi = item_hi;                      // first item that starts at or after w
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (wprefix[mid] < w) lo = mid + 1; else hi = mid; }
     split[b] = b == grid ? (int)item_hi : (int)lo;
 }
 
@@ -251,10 +283,10 @@ struct GrArgs {
 };
 
 #ifdef IB_GROUP_TRACE       // tools/build_variants.py: per-warp cycle counts of the last launch (never in the product library)
-__device__ unsigned long long g_group_trace[256 * 17 * 6];      // warp 16 = producer
+__device__ unsigned long long g_group_trace[256 * 17 * 8];      // warp 16 = producer
 #define GTR_DECL unsigned long long tr_wait = 0, tr_math = 0, tr_store = 0, tr_pre = 0, tr_g0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tr_g0)); const long long tr_t0 = clock64(); long long tr_t = tr_t0
 #define GTR_ADD(acc) do { const long long now_ = clock64(); acc += now_ - tr_t; tr_t = now_; } while (0)
-#define GTR_FLUSH() do { if (lane == 0 && blockIdx.x < 256) { unsigned long long *o_ = g_group_trace + ((size_t)blockIdx.x * 17 + warp) * 6; o_[4] = tr_pre; { unsigned long long g1_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1_)); o_[5] = g1_ - tr_g0; } \
+#define GTR_FLUSH() do { if (lane == 0 && blockIdx.x < 256) { unsigned long long *o_ = g_group_trace + ((size_t)blockIdx.x * 17 + warp) * 8; o_[4] = tr_pre; { unsigned long long g1_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1_)); o_[5] = g1_ - tr_g0; o_[6] = tr_g0; o_[7] = g1_; } \
     o_[0] = tr_wait; o_[1] = tr_math; o_[2] = tr_store; o_[3] = clock64() - tr_t0; } } while (0)
 #else
 #define GTR_DECL do { } while (0)
@@ -405,11 +437,6 @@ __global__ void __launch_bounds__(GR_THREADS, 1) smooth_group_kernel(const __gri
                     }
 #pragma unroll
                     for (int t = 0; t < 4; ++t) av[t] = cf[t * 32 + lane];
-#ifdef IB_GROUP_AV_EARLY
-                    double av1[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) av1[t] = cf[(4 + t) * 32 + lane];
-#endif
                     if (!fields_full) {
                         // fields past nvar were not copied: stale shared memory
 #pragma unroll
@@ -431,11 +458,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) smooth_group_kernel(const __gri
                             // the second k-step's A fragments take the registers of the first's once its DMMAs are issued
                             if (s == 1) {
 #pragma unroll
-#ifdef IB_GROUP_AV_EARLY
-                                for (int t = 0; t < 4; ++t) av[t] = av1[t];
-#else
                                 for (int t = 0; t < 4; ++t) av[t] = cf[(4 + t) * 32 + lane];
-#endif
                             }
                             switch (bm >> (4 * s) & 15u) {
                             case 1: gr_blocks<1>(acc, av, b[s]); break;
@@ -511,7 +534,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) smooth_group_kernel(const __gri
 extern "C" int ib_debug_group_trace(unsigned long long *out, int nblk)
 {
     cudaDeviceSynchronize();
-    return (int)cudaMemcpyFromSymbol(out, g_group_trace, sizeof(unsigned long long) * 17 * 6 * nblk);
+    return (int)cudaMemcpyFromSymbol(out, g_group_trace, sizeof(unsigned long long) * 17 * 8 * nblk);
 }
 #endif
 
@@ -547,7 +570,7 @@ bool apply_group(Weighted &W, const double *dX, int64_t ldx, int nvar, double *d
     const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(item_hi - item_lo, sm_count()));
     if (P.split_lo != item_lo || P.split_hi != item_hi || P.split_grid != (int)grid) {
         P.split.alloc((size_t)grid + 1, s);
-        gr_split_kernel<<<(unsigned)cdiv(grid + 1, 128), 128, 0, s>>>(P.items.p, item_lo, item_hi, (int)grid, P.split.p);
+        gr_split_kernel<<<(unsigned)cdiv(grid + 1, 128), 128, 0, s>>>(P.wprefix.p, item_lo, item_hi, (int)grid, P.split.p);
         IB_LAUNCHED();
         P.split_lo = item_lo; P.split_hi = item_hi; P.split_grid = (int)grid;
     }

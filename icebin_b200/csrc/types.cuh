@@ -111,6 +111,7 @@ struct GroupPlan {
     int64_t nitems = 0, nchunks = 0;
     DBuf<int4> items;               // (first row, first chunk, end chunk, rows)
     DBuf<unsigned char> chunks;     // chunk records: columns, presence masks, dense coefficient table
+    DBuf<uint32_t> wprefix;         // [nitems + 1] running sum of the items' estimated cost
     DBuf<int> split;                // [split_grid + 1] first item of every CTA for the row block [split_lo, split_hi)
     int64_t split_lo = -1, split_hi = -1;
     int split_grid = 0;
