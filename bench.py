@@ -255,6 +255,9 @@ def more_single_gpu(torch, api, args, cfg, gcm, mats, X, YE, YA, stream, peak, n
         bms = 1e3 * (time.perf_counter() - t0)
         ms = ev_time(torch, lambda: IvEs.apply_dev(YE.data_ptr(), nvar, nvar, YI.data_ptr(), nvar, True, stream), max(3, nrep // 4))
         res["IvE_smoothed"] = dict(apply_stats(IvEs, ms), sigma=[50e3, 50e3, 100.0], build_ms=bms, force_conservation=True)
+        ms = ev_time(torch, lambda: IvEs.apply_dev(YE.data_ptr(), nvar, nvar, YI.data_ptr(), nvar, False, stream), max(3, nrep // 4))
+        res["IvE_smoothed_no_correction"] = dict(apply_stats(IvEs, ms), force_conservation=False,
+                                                 kernel="smooth_group_kernel (DMMA.8x8x4 blocks)")
         return res
     guarded("applies_alone", applies)
 

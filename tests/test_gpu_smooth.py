@@ -93,3 +93,38 @@ def test_smoothed_apply_nan_reaches_only_named_rows(cfg2):
     ok = np.ones(64, bool); ok[[7, 9]] = False
     Xc = X.copy(); Xc[7, bad] = 0.5; Xc[9, bad[0]] = 0.5
     np.testing.assert_allclose(Y[ok], (M @ Xc[ok].T).T, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("nvar", [34, 96, 100, 544])
+def test_group_kernel_field_counts_and_row_blocks(cfg2, nvar):
+    """The tensor-core group kernel at field counts that leave a consumer warp's 32-field strip partly empty (34, 100),
+    fill only some warps (96) or need a second tile (544), with a NaN in the last field; row blocks of the row-block entry
+    point agree bit for bit with the whole matrix through the same kernel."""
+    import scipy.sparse as sp
+    import torch
+    gg = make_gpu(cfg2)
+    em = cfg2["elevmask"][0]
+    Wg = gg.regrid_matrices(cfg2["sheets"][0].name, em, scale=True, correctA=True, sigma=(50e3, 50e3, 100.0)).matrix("IvE")
+    r, c, v = Wg.to_coo_dense()
+    M = sp.csr_matrix((v, (r, c)), shape=Wg.shape)
+    X = np.random.default_rng(nvar).uniform(-1, 1, (nvar, Wg.shape[1]))
+    Y = Wg.apply(X, force_conservation=False)
+    A = sp.csr_matrix((np.abs(v), (r, c)), shape=Wg.shape)
+    assert np.all(np.abs(Y - (M @ X.T).T) <= 1e-12 * (A @ np.abs(X).T).T + 1e-300)
+    X[nvar - 1, 17] = np.nan
+    Yn = Wg.apply(X, force_conservation=False)
+    hit = np.zeros(Wg.shape[0], bool)
+    hit[M.tocsc()[:, [17]].tocoo().row] = True
+    assert np.array_equal(np.isnan(Yn[nvar - 1]), hit) and np.array_equal(Yn[: nvar - 1], Y[: nvar - 1])
+    # row blocks (cell-major device buffers)
+    nrow, ncol = Wg.shape
+    dX = torch.tensor(np.ascontiguousarray(X.T), device="cuda")
+    dYa = torch.full((nrow, nvar), -7.0, dtype=torch.float64, device="cuda")
+    dYb = torch.full((nrow, nvar), -7.0, dtype=torch.float64, device="cuda")
+    Wg.apply_rows_dev(dX.data_ptr(), nvar, nvar, dYa.data_ptr(), nvar, 0, nrow)
+    cut = (nrow // 3) // 32 * 32
+    for lo, hi in ((0, cut), (cut, 2 * cut + 64), (2 * cut + 64, nrow)):
+        Wg.apply_rows_dev(dX.data_ptr(), nvar, nvar, dYb.data_ptr(), nvar, lo, hi)
+    torch.cuda.synchronize()
+    assert torch.equal(dYa.isnan(), dYb.isnan()) and torch.equal(dYa.nan_to_num(0.0), dYb.nan_to_num(0.0))
+    assert np.array_equal(np.isnan(dYa.cpu().numpy().T), np.isnan(Yn))

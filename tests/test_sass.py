@@ -66,3 +66,16 @@ def test_no_fused_multiply_add_in_the_spmm_kernels(apply_sass):
             assert "DFMA" not in body, name
             if "fixup" not in name:
                 assert "DMUL" in body and "DADD" in body, name
+
+
+def test_group_kernel_runs_on_the_fp64_tensor_path(apply_sass):
+    """smooth_group_kernel multiplies its 8 x 4 blocks with DMMA (unpredicated: a predicated-off DMMA still occupies the
+    pipe), hands the producer warpgroup's registers to the consumers and does not spill."""
+    _, funcs = apply_sass
+    mine = {k: v for k, v in funcs.items() if "smooth_group_kernel" in k}
+    assert mine
+    for name, body in mine.items():
+        assert "DMMA.8x8x4" in body, name
+        assert not re.search(r"@!?U?P\d+\s+DMMA", body), name + ": predicated DMMA"
+        assert "USETMAXREG.DEALLOC" in body and "USETMAXREG.TRY_ALLOC" in body, name
+        assert "STL" not in body and "LDL" not in body, name + ": register spills"
