@@ -54,6 +54,11 @@ def parse():
     ap.add_argument("--no-more", action="store_true", help="skip the secondary measurements (`more`)")
     ap.add_argument("--merge", default="peer", choices=["peer", "nccl"],
                     help="N>1: merge of the sheets' A/E contributions by the library's peer-memory kernels (default) or an NCCL all-reduce")
+    ap.add_argument("--trace", default="", help="diagnostics: with the IB_STEP_TRACE library, write <prefix>_rank<r>.npz (per-step time stamps)")
+    ap.add_argument("--no-merge", action="store_true", help="diagnostics, N>1: skip the merge (independent replicas)")
+    ap.add_argument("--spare", type=int, default=16, help="N>1: CTA slots the apply leaves free for the exchange kernels")
+    ap.add_argument("--xchg-blocks", type=int, default=32, help="N>1: 128-thread blocks of the exchange kernels")
+    ap.add_argument("--nbuf", type=int, default=8, help="N>1: result buffer sets (how many steps a merge may lag its apply)")
     return ap.parse_args()
 
 
@@ -456,7 +461,10 @@ def run_b200(args):
             # (as sum = Y * wM) and are rewritten: sum over owners / summed weights (multivec.cpp:35-81)
             peer = multi.PeerMerge([(gcm.nE, EvI), (gcm.nA, AvI)], nvar, dev, scaled=True)
             mergeA = peer
-            api.tune("stream_spare", 8)      # the small merge kernels need a free CTA slot next to the SpMM's resident grid
+            # the small merge kernels need free CTA slots next to the SpMM's resident grid, and no more blocks than slots:
+            # a block that finds none waits for the SpMM's CTAs to exit (measured: publish took one whole SpMM, 45 us)
+            api.tune("stream_spare", args.spare)
+            api.tune("xchg_blocks", args.xchg_blocks)
         else:
             # as in the coupler (IceCoupler.cpp:371-377, 445-457): UNSCALED EvI / AvI, pack + NCCL all-reduce + unpack
             rm_u = gcm.regrid_matrices(sh.name, em_host, scale=False, correctA=True)
@@ -465,11 +473,15 @@ def run_b200(args):
             merges = [multi.SheetMerge([(gcm.nE, EvI), (gcm.nA, AvI)], nvar, dev) for _ in range(4)]
             mergeA = merges[0]
         side = torch.cuda.Stream(device=dev, priority=-1)       # the small merge kernels go first when a CTA slot frees up
-        NBUF = 4            # result buffer sets: a merge may lag its SpMM by NBUF - 1 steps (absorbs the ranks' jitter)
+        # publish and gather on streams of their own: next to a running SpMM a publish takes about as long as the SpMM
+        # (its loads and its system-scope fence queue behind the SpMM's traffic), so publish(s + 1) has to overlap gather(s)
+        side2 = torch.cuda.Stream(device=dev, priority=-1)
+        NBUF = max(2, min(8, args.nbuf))            # result buffer sets: a merge may lag its SpMM by NBUF - 1 steps (absorbs the ranks' jitter)
         YEs = [YE] + [torch.empty_like(YE) for _ in range(NBUF - 1)]
         YAs = [YA] + [torch.empty_like(YA) for _ in range(NBUF - 1)]
         spmm_done = [torch.cuda.Event() for _ in range(NBUF)]
         merge_done = [torch.cuda.Event() for _ in range(NBUF)]
+        pub_done = [torch.cuda.Event() for _ in range(NBUF)]
 
     YE_p, YA_p = YE.data_ptr(), YA.data_ptr()
     # pre-built argument arrays for the C ABI (the per-step Python cost matters at a 60 us step)
@@ -485,6 +497,7 @@ def run_b200(args):
     if mergeA is not None and args.merge == "peer":
         _pa = [peer.args([YEs[k], YAs[k]]) for k in range(NBUF)]
         _side = _vp(side.cuda_stream)
+        _side2 = _vp(side2.cuda_stream)
     step_no = [0]
     fresh = [True] * 8         # no exchange pending on buffer set k (start of the run / of a captured graph)
 
@@ -501,12 +514,19 @@ def run_b200(args):
         fresh[k] = False
         check(_apply_many(2, _W2, _X, nvar, nvar, _Yp[k], _ld2, 1, _st))
         spmm_done[k].record(tstream)
+        if args.no_merge:
+            merge_done[k].record(tstream)
+            return
         side.wait_event(spmm_done[k])
         if args.merge == "peer":
-            peer.merge_raw(_pa[k][0], _pa[k][1], nvar, _side)
+            peer.publish_raw(_pa[k][0], _pa[k][1], nvar, _side)
+            pub_done[k].record(side)
+            side2.wait_event(pub_done[k])
+            peer.gather_raw(_pa[k][0], _pa[k][1], nvar, _side2)
+            merge_done[k].record(side2)
         else:
             merges[k].run([YEs[k], YAs[k]], side)
-        merge_done[k].record(side)
+            merge_done[k].record(side)
 
     def drain():
         if mergeA is not None:
@@ -551,6 +571,14 @@ def run_b200(args):
             graph = None
             torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    trace_on = bool(args.trace) and hasattr(lib(), "ib_debug_stream_steps")
+    if args.trace and not trace_on:
+        sys.stderr.write("bench.py: --trace needs the IB_STEP_TRACE library (tools/build_variants.py steptrace IB_STEP_TRACE)\n")
+    if trace_on:
+        torch.cuda.synchronize()
+        lib().ib_debug_stream_steps.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        lib().ib_debug_stream_steps(None, 0, 1)
+        x_step0 = peer.steps_done() if (world > 1 and args.merge == "peer") else 0
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -570,6 +598,19 @@ def run_b200(args):
     ev[1].record()
     torch.cuda.synchronize()
     sampler.active = False
+    if trace_on:
+        import numpy as _np
+        n = min(4096, args.steps)
+        st = _np.zeros((4096, 4), _np.uint64)
+        lib().ib_debug_stream_steps(st.ctypes.data_as(C.c_void_p), 4096, 0)
+        out = {"stream": st[:n], "ms_total": _np.array([ev[0].elapsed_time(ev[1])])}
+        if world > 1 and args.merge == "peer":
+            xs = _np.zeros((4096, 8), _np.uint64)
+            lib().ib_debug_xchg_steps.argtypes = [C.c_void_p, C.c_int]
+            lib().ib_debug_xchg_steps(xs.ctypes.data_as(C.c_void_p), 4096)
+            idx = (_np.arange(n) + x_step0) % 4096
+            out["xchg"] = xs[idx]
+        _np.savez("%s_rank%d.npz" % (args.trace, rank), **out)
     launches = api.launch_count() - l0
     if graph is not None:
         launches += (args.steps // GSTEPS) * launches_per_graph      # kernels replayed from the graph
@@ -681,8 +722,10 @@ def run_b200(args):
     alg = 12 * nnz + 8 * nvar * (nI_d + nE_d + nA_d)
     achieved = alg / (stack_ms * 1e-3) / 1e9
     if mergeA is not None:
-        how = ("ib_xchg_merge_dev: every rank publishes the rows of its shared cells in peer-mapped memory and gathers its owners' rows over NVLink "
-               "(two kernels, no collective call), on a side stream, overlapping the next step's SpMM; at most %d B published per rank and step"
+        how = ("ib_xchg_publish_dev / ib_xchg_gather_dev: every rank stores the rows of its shared cells into its peers' inboxes over NVLink and adds "
+               "up its own inbox (no collective call); publish and gather on two side streams (publish(s + 1) overlaps gather(s)), both overlapping "
+               "later steps' SpMMs; the SpMM leaves " + str(args.spare) + " CTA slots free, the exchange kernels run " + str(args.xchg_blocks) +
+               " blocks of 128 threads, " + str(NBUF) + " result buffer sets; at most %d B published per rank and step"
                if args.merge == "peer" else
                "NCCL all-reduce(sum) of the shared rows' unscaled sums on a side stream, overlapping the next step's SpMM, %d B per step")
         line_extra = {"merge": {"shared_E_cells": int(mergeA.parts[0]["nshared"]), "shared_A_cells": int(mergeA.parts[1]["nshared"]),

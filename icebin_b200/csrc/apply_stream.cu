@@ -358,6 +358,22 @@ __device__ __forceinline__ unsigned long long gtime()
 #else
 #define TRACE(slot) do { } while (0)
 #endif
+#ifdef IB_STEP_TRACE        // tools/build_variants.py: span of every launch (ring of 4096), for the multi-GPU step timeline
+__device__ unsigned long long g_st_steps[4096 * 4];      // released (min), main end (max), fix-up released (min), fix-up end (max)
+__device__ unsigned g_st_arrive[2];
+__device__ __forceinline__ unsigned long long st_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define STEP_BEGIN(which, idxvar) unsigned idxvar = 0; if (threadIdx.x == 0) { idxvar = (atomicAdd(&g_st_arrive[which], 1u) / gridDim.x) & 4095u; \
+    atomicMin(&g_st_steps[idxvar * 4 + 2 * (which)], st_now()); }
+#define STEP_END(which, idxvar) do { if (threadIdx.x == 0) atomicMax(&g_st_steps[idxvar * 4 + 2 * (which) + 1], st_now()); } while (0)
+#else
+#define STEP_BEGIN(which, idxvar) do { } while (0)
+#define STEP_END(which, idxvar) do { } while (0)
+#endif
 
 struct StreamArgs {
     const int4 *recs;           // StRec
@@ -404,7 +420,8 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) spmm_stream_fixup_kernel(const
     const int f = (int)(w % a.nstrip) * 64 + 2 * lane;
     if (mine) { r = __ldg(a.fixrows + w / a.nstrip); info = __ldg(a.rowinfo + r); }      // plan data: before the wait
     pdl_wait();
-    if (!mine || f >= a.nvar) return;
+    STEP_BEGIN(1, st_idx);
+    if (!mine || f >= a.nvar) { STEP_END(1, st_idx); return; }
     double2 t = make_double2(0.0, 0.0);
     const double *pb = a.partials + (int64_t)info.x * a.ldp + f;
     for (int q0 = 0; q0 < info.y; q0 += 8) {
@@ -418,12 +435,16 @@ __global__ void __launch_bounds__(FIX_WARPS * 32) spmm_stream_fixup_kernel(const
     }
     double *y = (r < a.nrow1 ? a.Y1 + (int64_t)r * a.ldy1 : a.Y2 + (int64_t)(r - a.nrow1) * a.ldy2) + f;
     *reinterpret_cast<double2 *>(y) = t;
+    STEP_END(1, st_idx);
 }
 
 template <int NACC>
 __global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_constant__ StreamArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+#ifdef IB_STEP_TRACE
+    unsigned &st_idx_s = *reinterpret_cast<unsigned *>(smem_raw + ST_HDR - 8);      // the header's tail is unused
+#endif
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
     uint64_t *empty = full + a.nstage;
     unsigned char *data = smem_raw + 256;           // 2*nstage*8 <= 256
@@ -455,6 +476,12 @@ __global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_consta
         int c_next = (lane < ST_ROWS && jb + lane < je) ? __ldg(a.cols + jb + lane) : 0;
         pdl_wait();                                 // X may be the previous kernel's output
         TRACE(1);
+#ifdef IB_STEP_TRACE
+        if (lane == 0) {
+            st_idx_s = (atomicAdd(&g_st_arrive[0], 1u) / gridDim.x) & 4095u;
+            atomicMin(&g_st_steps[st_idx_s * 4], st_now());
+        }
+#endif
         for (int j = jb; j < je; j += ST_ROWS) {
             const int nr = min(ST_ROWS, je - j);
             const int c = c_next;
@@ -547,6 +574,9 @@ __global__ void __launch_bounds__(288, 3) spmm_stream_kernel(const __grid_consta
         if (++stage == a.nstage) { stage = 0; phase ^= 1u; }
     }
     if (warp == 0) { TRACE(3); TRACE(4); }
+#ifdef IB_STEP_TRACE
+    if (threadIdx.x == 0) atomicMax(&g_st_steps[st_idx_s * 4 + 1], st_now());
+#endif
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -619,6 +649,23 @@ bool apply_stream(Weighted &M1, Weighted *M2, const double *dX, int64_t ldx, int
     return true;
 }
 
+#ifdef IB_STEP_TRACE
+extern "C" int ib_debug_stream_steps(unsigned long long *out, int n, int reset)
+{
+    cudaDeviceSynchronize();
+    int rc = 0;
+    if (out) rc = (int)cudaMemcpyFromSymbol(out, g_st_steps, sizeof(unsigned long long) * 4 * n);
+    if (reset) {
+        static unsigned long long init[4096 * 4];
+        for (int i = 0; i < 4096; ++i) { init[4 * i] = init[4 * i + 2] = ~0ull; init[4 * i + 1] = init[4 * i + 3] = 0; }
+        unsigned zero[2] = {0, 0};
+        cudaMemcpyToSymbol(g_st_steps, init, sizeof init);
+        cudaMemcpyToSymbol(g_st_arrive, zero, sizeof zero);
+        cudaDeviceSynchronize();
+    }
+    return rc;
+}
+#endif
 #ifdef IB_STREAM_TRACE
 extern "C" int ib_debug_stream_trace(unsigned long long *out, int nblk)
 {

@@ -200,6 +200,7 @@ int ib_tune(const char *key, int value)
     else if (k == "use_stream") g_tune.use_stream = value != 0;
     else if (k == "use_gc") g_tune.use_gc = value != 0;
     else if (k == "use_group") g_tune.use_group = value != 0;
+    else if (k == "xchg_blocks") g_tune.xchg_blocks = std::max(1, std::min(value, 1024));
     else if (k == "hntr_generic") g_tune.hntr_generic = value != 0;
     else fail(IB_ERR_ARG, "ib_tune: unknown key '%s'", key);
     return IB_OK;

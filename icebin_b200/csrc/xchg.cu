@@ -11,17 +11,20 @@
 // 4 KB per (cell, other owner) at 512 fields instead of an all-reduce of every shared row through every rank.
 //
 // Protocol (PUSH: data and flags travel as posted stores over NVLink; every wait polls LOCAL memory, so no rank ever
-// pays a load round trip over the link).  Rank r's region holds, for every peer q, an inbox [2 parities][shared rows] and
+// pays a load round trip over the link).  Rank r's region holds, for every peer q, an inbox [4 slots][shared rows] and
 // two counters:
 //   ready[q] = t : q has delivered its rows of steps < t into r's inbox        (stored remotely by q's publish kernel)
-//   done[q]  = t : q has finished gathering steps < t out of ITS inbox, i.e. r may overwrite q's inbox parity again
+//   done[q]  = t : q has finished gathering steps < t out of ITS inbox, i.e. r may overwrite q's inbox slot again
 //                                                                               (stored remotely by q's gather kernel)
-//   publish(step s): wait for done[q] >= s - 1 of every peer q that shares a cell (inbox parity s & 1 was last read in
-//   step s - 2), store this rank's row of every shared cell into the inbox of every other owner, fence (system scope),
+//   publish(step s): wait for done[q] >= s - 3 of every peer q that shares a cell (inbox slot s % 4 was last read in
+//   step s - 4: with two slots the ring publish(s) -> peers' gather(s) -> publish(s + 2) set the pace at 8 GPUs, 190 us per
+//   two steps), store this rank's row of every shared cell into the inbox of every other owner, fence (system scope),
 //   then set ready[me] = s + 1 in those peers;
 //   gather(step s): wait for ready[q] >= s + 1 of those peers, add own row and inbox rows in ascending rank order, scale;
 //   then set done[me] = s + 1 in the peers.
-// The step counter lives in device memory and is advanced by the gather kernel, so a captured graph replays.  Waits
+// Each kernel keeps its own step counter in device memory (advanced by its last block), so a captured graph replays and
+// publish(s + 1) may run -- on another stream -- while gather(s) is still adding: they touch different inbox parities and
+// different result buffers, and a publish starved by a concurrent SpMM then no longer delays the gathers.  Waits
 // give up after XCHG_TIMEOUT_NS (a dead peer must not hang the GPU); ib_xchg_status() reports it.
 //
 // Spinning kernels of DIFFERENT ranks must run on different GPUs (nothing guarantees co-scheduling on one device).
@@ -36,7 +39,8 @@ namespace ib {
 
 constexpr unsigned long long XCHG_TIMEOUT_NS = 4000000000ull;
 constexpr int XCHG_MAX_RANKS = 64;
-constexpr int XCHG_MAX_BLOCKS = 48;
+constexpr int XCHG_THREADS = 128;
+constexpr int XCHG_DEPTH = 4;          // inbox slots per peer: publish(s + XCHG_DEPTH) is what has to wait for the peers' gather(s)
 
 struct XHdr {
     unsigned long long ready[XCHG_MAX_RANKS], done[XCHG_MAX_RANKS];
@@ -56,12 +60,12 @@ struct Xchg {
     int rank = 0, nranks = 1, device = 0;
     int64_t total = 0, ldb = 0;
     std::vector<XPart> parts;
-    void *region = nullptr;                 // XHdr + inbox[2][nranks][total][ldb], cudaMalloc (IPC-exportable)
+    void *region = nullptr;                 // XHdr + inbox[XCHG_DEPTH][nranks][total][ldb], cudaMalloc (IPC-exportable)
     size_t region_bytes = 0;
     void *peer[XCHG_MAX_RANKS] = {};        // mapped regions (peer[rank] = region)
     bool ipc_opened[XCHG_MAX_RANKS] = {};
     uint64_t reads_mask = 0, readers_mask = 0;     // ranks whose rows this rank gathers / that gather this rank's rows
-    DBuf<unsigned long long> step;          // [1]
+    DBuf<unsigned long long> step;          // [2] steps gathered, steps published
     DBuf<unsigned> counters;                // [2] last-block counters of the two kernels
     DBuf<int> err;                          // [1] sticky: 1 = a wait timed out
     DBuf<unsigned long long> d_peer;        // [nranks] device copy of the mapped region addresses
@@ -91,6 +95,14 @@ __device__ __forceinline__ unsigned long long xtime()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+#ifdef IB_STEP_TRACE        // tools/: per-step time stamps of the two kernels (block 0), ring of 4096 steps
+__device__ unsigned long long g_x_steps[4096 * 8];       // publish: start, waited, stored, flags set; gather: start, waited, end
+#define XTR(s, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_x_steps[((s) & 4095ull) * 8 + (slot)] = xtime(); } while (0)
+#define XTR_LAST(s, slot) do { g_x_steps[((s) & 4095ull) * 8 + (slot)] = xtime(); } while (0)
+#else
+#define XTR(s, slot) do { } while (0)
+#define XTR_LAST(s, slot) do { } while (0)
+#endif
 // thread 0 of the block polls, in THIS rank's header, counter `field` (0 ready, 1 done) of every peer in `mask`
 __device__ void xchg_wait(const XHdr *mine, uint64_t mask, int field, unsigned long long want, int *err)
 {
@@ -134,13 +146,31 @@ __device__ __forceinline__ double *xchg_inbox(unsigned long long region, int par
     return reinterpret_cast<double *>(region + sizeof(XHdr)) + ((int64_t)parity * nranks + from) * total * ldb;
 }
 
+// The waits as kernels of their own (one warp): a publish or gather that spins for a late peer would hold the few CTA
+// slots a concurrent SpMM leaves free -- the very slots the OTHER kernel of the pair needs to make that peer's wait end.
+// The kernels proper repeat the wait, which is then already satisfied.
+__global__ void xchg_wait_kernel(const XArgs a, int field)
+{
+    XHdr *mine = reinterpret_cast<XHdr *>(a.peers[a.rank]);
+    if (field) {
+        const unsigned long long s = a.step[1];
+        if (s >= XCHG_DEPTH) xchg_wait(mine, a.readers_mask, 1, s - XCHG_DEPTH + 1, a.err);
+    } else {
+        xchg_wait(mine, a.reads_mask, 0, a.step[0] + 1, a.err);
+    }
+}
+
 // one thread per (shared cell of any part, field pair), four items in flight per thread: this rank's row of the cell
 // is stored into the inbox of every other owner
-__global__ void __launch_bounds__(256) xchg_publish_kernel(const XArgs a)
+// (128-thread blocks: next to a running SpMM the two kernels share the few CTA slots it leaves free -- 20 K registers each --
+// and a 256-thread publish block and a gather block did not fit one slot together, so publish and gather took turns)
+__global__ void __launch_bounds__(XCHG_THREADS) xchg_publish_kernel(const XArgs a)
 {
-    const unsigned long long s = *a.step;
+    const unsigned long long s = a.step[1];
     XHdr *mine = reinterpret_cast<XHdr *>(a.peers[a.rank]);
-    if (s >= 2) xchg_wait(mine, a.readers_mask, 1, s - 1, a.err);      // the peers have finished reading parity s & 1
+    XTR(s, 0);
+    if (s >= XCHG_DEPTH) xchg_wait(mine, a.readers_mask, 1, s - XCHG_DEPTH + 1, a.err);      // the peers have finished reading slot s % DEPTH
+    XTR(s, 1);
     const int nv2 = (a.nvar + 1) / 2;
     const int64_t work = a.total * nv2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -170,36 +200,41 @@ __global__ void __launch_bounds__(256) xchg_publish_kernel(const XArgs a)
         for (int u = 0; u < 4; ++u)
             for (uint64_t o = own[u]; o; o &= o - 1) {       // posted stores over NVLink
                 const int q = __ffsll((long long)o) - 1;
-                *reinterpret_cast<double2 *>(xchg_inbox(a.peers[q], (int)(s & 1), a.nranks, a.rank, a.total, a.ldb) + at[u]) = v[u];
+                *reinterpret_cast<double2 *>(xchg_inbox(a.peers[q], (int)(s % XCHG_DEPTH), a.nranks, a.rank, a.total, a.ldb) + at[u]) = v[u];
             }
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(a.counters, 1u) == gridDim.x - 1) {
         a.counters[0] = 0;
+        XTR_LAST(s, 2);
         __threadfence_system();
         for (uint64_t o = a.readers_mask; o; o &= o - 1) {
             const int q = __ffsll((long long)o) - 1;
             st_release_sys(reinterpret_cast<XHdr *>(a.peers[q])->ready + a.rank, s + 1);
         }
+        XTR_LAST(s, 3);
+        a.step[1] = s + 1;
     }
 }
 
 // one thread per (cell, field pair): a shared cell's value is the sum over its owners, in ascending rank order, of this
 // rank's own row and the rows in its inbox (all local memory), times 1 / (summed weights); unscaled parts also divide
 // the rows of unshared cells by their own weight
-__global__ void __launch_bounds__(256) xchg_gather_kernel(const XArgs a)
+__global__ void __launch_bounds__(XCHG_THREADS) xchg_gather_kernel(const XArgs a)
 {
     const unsigned long long s = *a.step;
     XHdr *mine = reinterpret_cast<XHdr *>(a.peers[a.rank]);
+    XTR(s, 4);
     xchg_wait(mine, a.reads_mask, 0, s + 1, a.err);
+    XTR(s, 5);
     const int nv2 = (a.nvar + 1) / 2;
     // work items: every local row of an unscaled part, only the shared cells of a scaled part
     int64_t cum[XCHG_MAX_PARTS + 1];
     cum[0] = 0;
     for (int p = 0; p < a.nparts; ++p) cum[p + 1] = cum[p] + (a.part[p].scaled ? a.part[p].nshared : a.part[p].nrow);
     const int64_t work = cum[a.nparts] * nv2;
-    const double *inbox0 = xchg_inbox(a.peers[a.rank], (int)(s & 1), a.nranks, 0, a.total, a.ldb);
+    const double *inbox0 = xchg_inbox(a.peers[a.rank], (int)(s % XCHG_DEPTH), a.nranks, 0, a.total, a.ldb);
     const int64_t per_rank = a.total * a.ldb;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t g = t / nv2;
@@ -245,6 +280,7 @@ __global__ void __launch_bounds__(256) xchg_gather_kernel(const XArgs a)
             const int q = __ffsll((long long)o) - 1;
             st_release_sys(reinterpret_cast<XHdr *>(a.peers[q])->done + a.rank, s + 1);
         }
+        XTR_LAST(s, 6);
         *a.step = s + 1;
     }
 }
@@ -273,8 +309,10 @@ void xchg_publish(Xchg &x, double *const *dY, const int64_t *ldy, int nvar, cuda
     XArgs a = make_args(x, dY, ldy, nvar);
     // few blocks, several items per thread: the kernels usually run in the CTA slots a resident SpMM grid leaves free
     const int64_t work = std::max<int64_t>(1, x.total * ((nvar + 1) / 2));
-    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(work, 256 * 4), XCHG_MAX_BLOCKS);
-    xchg_publish_kernel<<<grid, 256, 0, s>>>(a);
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(work, XCHG_THREADS * 4), g_tune.xchg_blocks);
+    xchg_wait_kernel<<<1, 32, 0, s>>>(a, 1);
+    IB_LAUNCHED();
+    xchg_publish_kernel<<<grid, XCHG_THREADS, 0, s>>>(a);
     IB_LAUNCHED();
 }
 void xchg_gather(Xchg &x, double *const *dY, const int64_t *ldy, int nvar, cudaStream_t s)
@@ -284,8 +322,10 @@ void xchg_gather(Xchg &x, double *const *dY, const int64_t *ldy, int nvar, cudaS
     for (auto &P : x.parts) rows += P.scaled ? P.nshared : P.nrow;
     const int64_t work = std::max<int64_t>(1, rows * ((nvar + 1) / 2));
     const bool all_scaled = std::all_of(x.parts.begin(), x.parts.end(), [](XPart const &P) { return P.scaled != 0; });
-    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(work, 256 * 4), all_scaled ? XCHG_MAX_BLOCKS : 2 * sm_count());
-    xchg_gather_kernel<<<grid, 256, 0, s>>>(a);
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(work, XCHG_THREADS * 4), all_scaled ? g_tune.xchg_blocks : 4 * sm_count());
+    xchg_wait_kernel<<<1, 32, 0, s>>>(a, 0);
+    IB_LAUNCHED();
+    xchg_gather_kernel<<<grid, XCHG_THREADS, 0, s>>>(a);
     IB_LAUNCHED();
 }
 
@@ -319,11 +359,11 @@ int ib_xchg_create(ib_xchg **out, int rank, int nranks, int nparts, const int64_
         x.parts[p].off = x.total;
         x.total += nshared[p];
     }
-    x.region_bytes = sizeof(XHdr) + (size_t)2 * nranks * std::max<int64_t>(x.total, 1) * x.ldb * sizeof(double);
+    x.region_bytes = sizeof(XHdr) + (size_t)XCHG_DEPTH * nranks * std::max<int64_t>(x.total, 1) * x.ldb * sizeof(double);
     IB_CUDA(cudaMalloc(&x.region, x.region_bytes));
     IB_CUDA(cudaMemset(x.region, 0, x.region_bytes));
     x.peer[rank] = x.region;
-    x.step.alloc(1, x.stream); x.step.zero();
+    x.step.alloc(2, x.stream); x.step.zero();
     x.counters.alloc(2, x.stream); x.counters.zero();
     x.err.alloc(1, x.stream); x.err.zero();
     x.d_peer.alloc((size_t)nranks, x.stream);
@@ -526,5 +566,13 @@ int64_t ib_xchg_plan(int nranks, const int64_t *const *ids, const int64_t *n, in
     return k;
     X_CATCH
 }
+
+#ifdef IB_STEP_TRACE
+int ib_debug_xchg_steps(unsigned long long *out, int n)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_x_steps, sizeof(unsigned long long) * 8 * n);
+}
+#endif
 
 }   // extern "C"

@@ -278,6 +278,12 @@ class PeerMerge:
     def merge_raw(self, yp, ld, nvar, stream):
         self._check(self._lib.ib_xchg_merge_dev(self._h, yp, ld, nvar, stream))
 
+    def publish_raw(self, yp, ld, nvar, stream):
+        self._check(self._lib.ib_xchg_publish_dev(self._h, yp, ld, nvar, stream))
+
+    def gather_raw(self, yp, ld, nvar, stream):
+        self._check(self._lib.ib_xchg_gather_dev(self._h, yp, ld, nvar, stream))
+
     def publish(self, Ys, stream=0):
         yp, ld = self._args(Ys)
         self._check(self._lib.ib_xchg_publish_dev(self._h, yp, ld, Ys[0].shape[1], stream or None))
