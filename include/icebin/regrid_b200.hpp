@@ -197,6 +197,18 @@ public:
         std::vector<int64_t> ld(ldy.begin(), ldy.end());
         ib_check(ib_xchg_merge_dev(h, dY.data(), ld.data(), nvar, stream));
     }
+    /** The two halves of merge() for hosts that pipeline batches: publish(s + 1) may run on another stream while gather(s)
+        is still adding (each kernel keeps its own step counter); gather(s) has to follow publish(s) of the same buffers. */
+    void publish(std::vector<double *> const &dY, std::vector<long> const &ldy, int nvar, void *stream = nullptr)
+    {
+        std::vector<int64_t> ld(ldy.begin(), ldy.end());
+        ib_check(ib_xchg_publish_dev(h, dY.data(), ld.data(), nvar, stream));
+    }
+    void gather(std::vector<double *> const &dY, std::vector<long> const &ldy, int nvar, void *stream = nullptr)
+    {
+        std::vector<int64_t> ld(ldy.begin(), ldy.end());
+        ib_check(ib_xchg_gather_dev(h, dY.data(), ld.data(), nvar, stream));
+    }
     void status() { ib_check(ib_xchg_status(h)); }
 };
 

@@ -201,11 +201,13 @@ int ib_merge_unpack_dev(double *dY, int64_t ldy, int32_t nvar, int64_t nrow, con
 
 /* ---- The same merge across GPUs over NVLink peer memory (one rank = one process = one GPU = one ice sheet) ----------
  * Replaces the MPI gather to the GCM root + VectorMultivec merge (modele/GCMCoupler_ModelE.cpp:761-793, multivec.cpp:35-81)
- * for results that stay in HBM: a rank publishes the rows of its shared cells in a buffer its peers have mapped (CUDA IPC)
- * and gathers, for every shared cell it holds, the owners' rows with plain loads over NVLink, added in ascending rank order
- * (the same bits on every rank), times 1 / (summed weights); rows of cells no other sheet touches are divided by their own
- * weight.  Two kernels per step, no host round trip, capturable in a CUDA graph; a step counter in device memory and
- * ready / done flags in the publisher's memory order the ranks (waits give up after 4 s: ib_xchg_status).
+ * for results that stay in HBM: a rank publishes the rows of its shared cells by storing them into the inboxes of the cells'
+ * other owners (their memory is mapped with CUDA IPC; posted stores over NVLink, four inbox slots per peer) and gathers, for
+ * every shared cell it holds, its own row and the rows in its inbox, added in ascending rank order (the same bits on every
+ * rank), times 1 / (summed weights); rows of cells no other sheet touches are divided by their own weight.  No host round
+ * trip, capturable in a CUDA graph; step counters in device memory (one per kernel: ib_xchg_publish_dev of step s + 1 may
+ * run on another stream while ib_xchg_gather_dev of step s is still adding) and ready / done counters in the RECEIVER's
+ * memory order the ranks: every wait polls local memory (waits give up after 4 s: ib_xchg_status).
  *
  *   host (all ranks):  gather every rank's dims[0] ids  ->  ib_xchg_plan  ->  ib_xchg_create  ->  all-gather the handles
  *                      ->  ib_xchg_open  ->  ib_xchg_set_part (per grid: E, A)  ->  ib_xchg_merge_dev every step.
