@@ -726,6 +726,7 @@ __global__ void __launch_bounds__(512) cons_scale_kernel(const double *__restric
     __shared__ double fac_s[4];
     const int rg = threadIdx.x >> 2, fi = threadIdx.x & 3;
     const int f = blockIdx.x * 4 + fi;
+    pdl_launch_dependents();             // the apply that follows may set itself up; it waits before it reads As
     double sa = 0, sb = 0;
     if (f < nvar) {
 #pragma unroll 9

@@ -29,11 +29,11 @@
 // at 5 km / 512 fields (tools/group_trace.py, 77 us per CTA): DMMA issue on a saturated pipe 45 us (= the 3.3 M DMMA at
 // the measured rate), the loads / checks / addressing ahead of them 19 us (issue-bound: the four warps of a scheduler
 // move in step, so this does not overlap the other warps' DMMA), stores 7 us, waiting for a stage 6 us.  The CTAs get
-// equal shares of a fitted cost (item, chunk, block), 72 .. 85 us; the kernel takes 87 us = 0.53 of the HBM roofline.
+// equal shares of a fitted cost (item, chunk, block), 72 .. 85 us; the kernel takes 84 us = 0.54 of the HBM roofline.
 // History: every warp its own pipeline with 512-byte copies 380 us -> CTA ring, 16-row items, DFMA 182 us -> DMMA 139 us
 // -> A fragments before the first DMMA + 112 registers for the consumers (setmaxnreg) 105 us -> switch instead of
 // predicates 102 us -> CTA shares read from a table instead of a binary search at the head of every CTA 99 us -> shares
-// by fitted cost 87 us.
+// by fitted cost 87 us -> programmatic dependent launch 84 us.
 #include <algorithm>
 #include <mutex>
 
@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) smooth_group_kernel(const __gri
     if (warp >= 16) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
         if (warp > 16 || i0 >= i1) return;
+        pdl_wait();                      // X may be the previous kernel's output (the corrected copy of the input)
         // ===== producer: one stage per chunk; lane k < ncols copies the X row of column k, lane 31 the chunk record.
         // The column ids of a stage are loaded one stage ahead, so the only thing the producer ever waits for is a
         // free stage.
@@ -568,14 +569,29 @@ bool apply_group(Weighted &W, const double *dX, int64_t ldx, int nvar, double *d
     const int64_t item_lo = row_lo / GR_R, item_hi = std::min<int64_t>(P.nitems, cdiv(row_hi, GR_R));
     if (item_lo >= item_hi) return true;
     const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(item_hi - item_lo, sm_count()));
+    bool fresh_split = false;
     if (P.split_lo != item_lo || P.split_hi != item_hi || P.split_grid != (int)grid) {
+        fresh_split = true;
         P.split.alloc((size_t)grid + 1, s);
         gr_split_kernel<<<(unsigned)cdiv(grid + 1, 128), 128, 0, s>>>(P.wprefix.p, item_lo, item_hi, (int)grid, P.split.p);
         IB_LAUNCHED();
         P.split_lo = item_lo; P.split_hi = item_hi; P.split_grid = (int)grid;
     }
     GrArgs a{P.items.p, P.chunks.p, P.split.p, ntile, tw, nstage, dX, ldx, nvar, dY, ldy};
-    smooth_group_kernel<<<(unsigned)grid, GR_THREADS, smem, s>>>(a);
+    // programmatic dependent launch: behind a kernel that triggers it (cons_scale_kernel) the CTAs set themselves up --
+    // barriers, register hand-over, their share of the items -- while that kernel still runs; the producer waits for it
+    // before the first copy of X.  Not on the call that has just launched gr_split_kernel: every thread reads its table.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(GR_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = fresh_split ? 0 : 1;
+    IB_CUDA(cudaLaunchKernelEx(&cfg, smooth_group_kernel, a));
     IB_LAUNCHED();
     return true;
 }
