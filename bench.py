@@ -56,8 +56,8 @@ def parse():
                     help="N>1: merge of the sheets' A/E contributions by the library's peer-memory kernels (default) or an NCCL all-reduce")
     ap.add_argument("--trace", default="", help="diagnostics: with the IB_STEP_TRACE library, write <prefix>_rank<r>.npz (per-step time stamps)")
     ap.add_argument("--no-merge", action="store_true", help="diagnostics, N>1: skip the merge (independent replicas)")
-    ap.add_argument("--spare", type=int, default=16, help="N>1: CTA slots the apply leaves free for the exchange kernels")
-    ap.add_argument("--xchg-blocks", type=int, default=32, help="N>1: 128-thread blocks of the exchange kernels")
+    ap.add_argument("--spare", type=int, default=24, help="N>1: CTA slots the apply leaves free for the exchange kernels")
+    ap.add_argument("--xchg-blocks", type=int, default=64, help="N>1: 128-thread blocks of the exchange kernels")
     ap.add_argument("--nbuf", type=int, default=8, help="N>1: result buffer sets (how many steps a merge may lag its apply)")
     return ap.parse_args()
 

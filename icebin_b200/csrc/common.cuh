@@ -51,7 +51,9 @@ constexpr int IB_MAX_DEVICES = 64;
 // performance knobs (ib_tune): never change results
 struct Tune {
     int stream_bps = 3;          // CTAs per SM of spmm_stream_kernel
-    int stream_spare = 0;        // CTA slots spmm_stream_kernel leaves free (room for a concurrent small kernel, e.g. the merge)
+    int stream_spare = 24;       // CTA slots spmm_stream_kernel leaves free: a grid that fills EVERY slot (444 CTAs) runs 62 us, one that
+                                 // leaves 8 / 24 / 48 free 59.0 / 58.0 / 57.1 us (tools/stream_sweep.py --spare); also the room a concurrent
+                                 // small kernel needs (the multi-GPU exchange)
     int tma_bps = 4;             // CTAs per SM of spmm_tma_kernel
     int gc_nq = 0;               // spmm_gc_kernel: 64-field groups per lane (0: by nvar)
     int use_stream = 1;          // one-pass kernel for wide matrices

@@ -1,6 +1,6 @@
 """Times the coupling-step applies (512 fields, Greenland 5 km): the stacked [EvI; AvI] one-pass apply, EvI alone and
-AvI alone, back to back with CUDA events, for each value of the `stream_bps` knob.  One JSON line per setting.
-Usage: python tools/stream_sweep.py [bps ...]        (also: --once STACK|EvI|AvI for a short run under ncu)"""
+AvI alone, back to back with CUDA events, for each value of the `stream_bps` (and `stream_spare`) knob.  One JSON line
+per setting.  Usage: python tools/stream_sweep.py [bps ...] [--spare s ...]   (also: --once STACK|EvI|AvI for ncu)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -36,10 +36,15 @@ if once:
     torch.cuda.synchronize()
     print("ok", once)
     sys.exit(0)
-for bps in ([int(a) for a in args] or [4]):
+spares = [0]
+if "--spare" in args:                       # e.g. `3 --spare 0 8 16 24`: CTA slots the one-pass kernel leaves free
+    k = args.index("--spare")
+    spares, args = [int(a) for a in args[k + 1:]], args[:k]
+for bps, spare in [(b, sp) for b in ([int(a) for a in args] or [4]) for sp in spares]:
     api.tune("stream_bps", bps)
     api.tune("tma_bps", bps)
-    out = {"bps": bps}
+    api.tune("stream_spare", spare)
+    out = {"bps": bps, "spare": spare}
     for name, (fn, byt, nnz) in cases.items():
         for _ in range(5):
             fn()
