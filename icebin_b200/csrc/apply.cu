@@ -899,7 +899,7 @@ void apply_dev(Weighted &W, const double *dX, int64_t ldx, int nvar, double *dY,
         }
         return;
     }
-    // tall matrices with longer rows that share columns (sigma-smoothed IvE / IvA): register-blocked groups of 16 rows
+    // tall matrices with longer rows that share columns (sigma-smoothed IvE / IvA): dense 8 x 4 blocks of 32-row items on the fp64 tensor-core path
     if (g_tune.use_group && !P.gc && P.max_row_len <= 128 && apply_group(W, dX, ldx, nvar, dY, ldy, rlo, rhi, s)) return;
     // X-stationary path: tall matrix, few columns, no long rows
     if (vec2 && !ranged && W.ncol > 0 && W.nrow >= 8 * W.ncol && P.max_row_len <= 256 && nvar >= 8 && 2 * W.nnz >= 3 * W.nrow) {

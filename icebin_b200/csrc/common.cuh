@@ -58,7 +58,7 @@ struct Tune {
     int gc_nq = 0;               // spmm_gc_kernel: 64-field groups per lane (0: by nvar)
     int use_stream = 1;          // one-pass kernel for wide matrices
     int use_gc = 1;              // distinct-column group kernel for short-row matrices
-    int use_group = 1;           // register-blocked group kernel for tall matrices with ~16 nonzeros per row
+    int use_group = 1;           // tensor-core group kernel for tall matrices with ~16 nonzeros per row that share columns
     int xchg_blocks = 96;        // 128-thread blocks of the two exchange kernels (<= the CTA slots a concurrent SpMM leaves free, or they wait for its CTAs to exit)
     int hntr_generic = 0;        // Hntr: always the generic kernels (skip the int16 / constant-weight fast path)
 };

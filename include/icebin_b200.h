@@ -53,7 +53,7 @@ int ib_set_device(int device);
 int64_t ib_launch_count(void);
 /* Performance knobs; results never depend on them.  Keys: "stream_bps", "tma_bps" (CTAs per SM of the one-pass / ring
  * SpMM kernels, 1..8), "stream_spare" (CTA slots the one-pass kernel leaves free -- default 24: faster than a grid that needs every slot, and room for a concurrent small kernel -- 0..64), "gc_nq" (64-field groups per lane of the distinct-column kernel: 0 = by nvar, 1, 2, 4),
- * "use_stream", "use_gc", "use_group" (0 = route around the one-pass / distinct-column / register-blocked group kernel), "hntr_generic" (1 = Hntr
+ * "use_stream", "use_gc", "use_group" (0 = route around the one-pass / distinct-column / tensor-core group kernel), "hntr_generic" (1 = Hntr
  * always takes its generic kernels), "xchg_blocks" (128-thread blocks of the two ib_xchg_* kernels, default 96: set it to the CTA slots a concurrent apply leaves
  * free -- "stream_spare" -- or the exchange waits for that apply's CTAs to exit). */
 int ib_tune(const char *key, int value);
