@@ -46,6 +46,7 @@ namespace ib {
 constexpr int GR_R = 32;                 // rows per item (four 8-row m-tiles)
 constexpr int GR_CH = 8;                 // columns per chunk (two k-steps of 4)
 constexpr int GR_MAXD = 128;             // distinct columns per item the plan accepts
+constexpr int64_t GR_MAX_ITEMS = 3500000; // an item costs at most (1140 + 16 * (491 + 8 * 69)) / 16 < 1200 units: sum < 2^32
 // chunk record: ncols, block mask (bit 4*kstep + mtile), done mask (bit mtile), pad | cols[8] | rowmask[8] | coef[kstep 2][mtile 4][lane 32]
 constexpr int GR_OFF_COLS = 16, GR_OFF_RMASK = GR_OFF_COLS + 4 * GR_CH, GR_OFF_COEF = GR_OFF_RMASK + 4 * GR_CH;
 constexpr int GR_REC = GR_OFF_COEF + 8 * GR_CH * GR_R;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(128) gr_emit_kernel(const int32_t *__restrict_
         for (int q = lane; q < nch; q += 32)
             wq += 491u + 69u * (uint32_t)__popc(reinterpret_cast<const int32_t *>(rec0 + (size_t)q * GR_REC)[1]);
         wq = __reduce_add_sync(0xffffffffu, wq);
-        if (lane == 0) weight[it] = wq + 1140u;
+        if (lane == 0) weight[it] = (wq + 1140u + 8u) >> 4;      // units of 16 ns: the running sum stays below 2^32 (GR_MAX_ITEMS)
     }
     // coefficients: lane = row; A-fragment order: [k-step][m-tile][(row % 8) * 4 + column % 4]
     for (int32_t e = jb; e < je; ++e) {
@@ -222,6 +223,7 @@ static bool make_group_plan(Weighted &W, cudaStream_t s)
     P.tried = true;
     if (W.nrow < 4 * GR_R || W.nnz < 4 * W.nrow || W.nrow < 4 * W.ncol || W.nnz >= (int64_t(1) << 31)) return false;
     const int64_t nitems = cdiv(W.nrow, GR_R);
+    if (nitems > GR_MAX_ITEMS) return false;
     DBuf<int> refuse(1, s);
     refuse.zero();
     DBuf<uint32_t> counts((size_t)nitems, s);
